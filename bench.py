@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/sec of the batched F1TENTH hot path on N B200s (weak scaling), with the
+roofline of the ray-march kernel and the CPU baseline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg2x2|cfg3|cfg5_B]
+    python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle C port), host cores
+    torchrun ... bench.py --gpus N ...        # one rank per GPU; envs shard, no data-path collective
+
+A "step" is one tick (Simulator.step + F110Env lap logic + auto-reset) over the workload's whole env
+batch on each GPU.  `value` = agent-steps/s over all GPUs with inputs resident in HBM, timed with CUDA
+events per step (L2 flushed between steps, outside the event pairs), max over ranks.  `e2e` = the same
+metric through the host-buffer API (f110_step_host): pinned H2D of the actions and D2H of the full
+observation (scans, state, collisions, done, laps) inside the timed region, every step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'agent-steps/sec (1080-beam scan)'
+UNIT = 'agent-steps/s'
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    'cfg2': dict(num_envs=4096, num_agents=1, num_beams=1080,
+                 desc='4096 single-agent envs, example_map, 1080 beams, random actions (BASELINE configs[1])'),
+    # the north_star target sentence: 4096 envs x 2 agents
+    'cfg2x2': dict(num_envs=4096, num_agents=2, num_beams=1080,
+                   desc='4096 envs x 2 agents, example_map, 1080 beams, random actions (north_star target)'),
+    'cfg3': dict(num_envs=16384, num_agents=2, num_beams=1080,
+                 desc='16384 envs x 2 agents with GJK, example_map, 1080 beams (BASELINE configs[2]; per-GPU share of configs[3])'),
+}
+for _b in (270, 540, 1080, 2160):
+    WORKLOADS['cfg5_%d' % _b] = dict(num_envs=32768, num_agents=1, num_beams=_b,
+                                     desc='beam sweep: 32768 single-agent envs, %d beams (BASELINE configs[4])' % _b)
+POSE_GAP = 23          # second agent 23 waypoints (~4.6 m) behind
+SEED = 12345
+FLUSH_BYTES = 256 << 20
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def ncu_traffic(workload):
+    """dram bytes per k_raymarch launch from the committed ncu capture summary, if one exists for this workload."""
+    p = os.path.join(ROOT, 'profiles', 'raymarch_ncu_summary.json')
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return d.get(workload, {}).get('dram_bytes_per_launch')
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {}
+        for nm in ('HwSlowdown', 'HwThermalSlowdown', 'SwThermalSlowdown', 'SwPowerCap', 'HwPowerBrakeSlowdown'):
+            for prefix in ('nvmlClocksEventReason', 'nvmlClocksThrottleReason'):
+                v = getattr(nv, prefix + nm, None)
+                if v is not None:
+                    names[nm] = v
+                    break
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        to_snake = {'HwSlowdown': 'hw_slowdown', 'HwThermalSlowdown': 'hw_thermal_slowdown',
+                    'SwThermalSlowdown': 'sw_thermal_slowdown', 'SwPowerCap': 'sw_power_cap',
+                    'HwPowerBrakeSlowdown': 'hw_power_brake_slowdown'}
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': float(self.max_mhz) if self.max_mhz else None,
+                'reasons': sorted(to_snake[r] for r in self.reasons), 'samples': len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------- CPU side
+def cpu_rollout_rate(workload, seconds_target, steps=None, warmup=0, threads=0):
+    """Times the oracle C port (the reference algorithm restated, -O2, no FMA) on the host cores with
+    the benchmark policy.  Returns dict(value, cores, sample, ...).  One env batch = a bounded sample of
+    the workload's envs; OS threads over envs (the reference itself is single-threaded numba)."""
+    import oracle
+    from f1tenth_gym_b200 import maps
+    w = WORKLOADS[workload]
+    A, B = w['num_agents'], w['num_beams']
+    cores = oracle.num_cores()
+    nthreads = threads if threads > 0 else cores
+    E = max(nthreads, min(w['num_envs'], 256 * nthreads // A))
+    omap = oracle.OracleMap.from_yaml(maps.resolve_map_path('example_map'), '.png')
+    sims = [oracle.OracleSim(omap, num_agents=A, num_beams=B) for _ in range(E)]
+    wp = maps.load_waypoints()
+    rng = np.random.default_rng(SEED)
+    for s in sims:
+        k = int(rng.integers(0, wp.shape[0]))
+        s.reset(np.stack([wp[(k - POSE_GAP * i) % wp.shape[0]] for i in range(A)]))
+    oracle.rollout(sims, 20, wp, POSE_GAP, SEED, nthreads)       # settle: mixed speeds, some resets
+    if steps is None:
+        t0 = time.perf_counter()
+        oracle.rollout(sims, 2, wp, POSE_GAP, SEED + 1, nthreads)
+        per_tick = (time.perf_counter() - t0) / 2
+        steps = max(3, int(seconds_target / max(per_tick, 1e-6)))
+    for t in range(warmup):
+        oracle.rollout(sims, 1, wp, POSE_GAP, SEED + 100 + t, nthreads)
+    t0 = time.perf_counter()
+    total, nlook = 0, 0
+    for t in range(steps):
+        n, l = oracle.rollout(sims, 1, wp, POSE_GAP, SEED + 1000 + t, nthreads)
+        total += n
+        nlook += l
+    dt = time.perf_counter() - t0
+    return {'value': total / dt, 'unit': UNIT, 'cores': nthreads, 'host_cores': cores,
+            'sample': '%d of the workload\'s %d envs x %d agents x %d ticks (%.1f s), oracle C port of the '
+                      'reference numba path, %d threads, noise off, same action/auto-reset policy'
+                      % (E, w['num_envs'], A, steps, dt, nthreads),
+            'seconds': dt, 'steps': steps, 'ms_per_step': 1e3 * dt / steps, 'envs': E,
+            'lookups_per_agent_step': nlook / max(total, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    r = cpu_rollout_rate(args.workload, None, steps=args.steps, warmup=args.warmup)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'description': w['desc'], 'map': 'example_map',
+                       'num_agents': w['num_agents'], 'num_beams': w['num_beams'],
+                       'sample_envs_per_step': r['envs']},
+            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                             'sample': r['sample']},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+            'note': 'the reference is pure Python+numba and cannot travel to the GPU box; this arm times the '
+                    'C restatement of its algorithm (oracle/f110_oracle.c, bit-exact vs the numba path on the '
+                    'golden trajectories) on all host cores'}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------- GPU side
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import f1tenth_gym_b200 as f110
+    from f1tenth_gym_b200.distributed import reduce_max_scalar
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world,
+                                device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    w = WORKLOADS[args.workload]
+    N, A, B = w['num_envs'], w['num_agents'], w['num_beams']
+    NA = N * A
+    K, W = args.steps, args.warmup
+
+    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, SEED + rank, num_envs=N, num_beams=B, device=dev)
+    sim.set_map(f110.maps.resolve_map_path('example_map'), '.png')
+    wp_np = f110.maps.load_waypoints()
+    wp = torch.from_numpy(wp_np).to(dev)
+    # initial poses keyed by GLOBAL env id so that the population does not depend on the GPU count
+    ks = np.array([np.random.default_rng(SEED + rank * N + e).integers(0, wp_np.shape[0]) for e in range(N)])
+    poses = np.stack([wp_np[(ks - POSE_GAP * i) % wp_np.shape[0]] for i in range(A)], axis=1)
+    sim.env_reset(poses)
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + 7919 * rank)
+    P = min(K + W, 1024)
+
+    def make_actions(n):
+        u = torch.rand((n, NA, 2), generator=gen, device=dev, dtype=torch.float64)
+        u[..., 0] = -0.4189 + 0.8378 * u[..., 0]      # steer ~ U[-0.4189, 0.4189]
+        u[..., 1] = 8.0 * u[..., 1]                   # speed ~ U[0, 8]
+        return u.contiguous()
+    pool = make_actions(P)
+    abuf = torch.zeros((NA, 2), dtype=torch.float64, device=dev)
+    sim.capture_graph(abuf, autoreset_poses=wp, pose_gap=POSE_GAP, autoreset_seed=SEED + rank, env_level=True)
+    launches_per_step = 5      # k_dynamics, k_raymarch, k_finalize, k_env_post_step, k_autoreset
+
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    for t in range(W):
+        abuf.copy_(pool[t % P])
+        sim.replay()
+    torch.cuda.synchronize(dev)
+
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    wall0 = time.perf_counter()
+    for t in range(K):
+        flush.zero_()                                 # evict L2 between timed steps (outside the event pair)
+        abuf.copy_(pool[(W + t) % P])
+        ev0[t].record()
+        sim.replay()
+        ev1[t].record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    step_ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
+    dev_ms_total = float(step_ms.sum())
+    dev_ms_total = reduce_max_scalar(dev_ms_total, dev)
+    value = K * NA * world / (dev_ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_raymarch): CUDA events around it, live, on its stream
+    prof_ticks = 20
+    kms = np.zeros(3)
+    for t in range(prof_ticks):
+        flush.zero_()
+        d = sim.step_profile(pool[t % P].view(N, A, 2))
+        sim.env_post_step()
+        sim.autoreset(wp, POSE_GAP, SEED + rank)
+        kms += np.array(d)
+    kms /= prof_ticks
+    counter = torch.zeros((1,), dtype=torch.int64, device=dev)
+    sim.c.lookup_counter = counter.data_ptr()
+    for t in range(prof_ticks):
+        sim.step(pool[(t + prof_ticks) % P].view(N, A, 2))
+        sim.env_post_step()
+        sim.autoreset(wp, POSE_GAP, SEED + rank)
+    torch.cuda.synchronize(dev)
+    sim.c.lookup_counter = None
+    L = counter.item() / float(prof_ticks * NA)                 # DT lookups per agent-step, this pose distribution
+    bytes_per_agent_step = 8.0 * L + 4.0 * B + 144.0            # fp64 DT element, fp32 range out, state/action/FIFO
+    bytes_per_launch = bytes_per_agent_step * NA
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_launch / (kms[1] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'k_raymarch', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': ncu_traffic(args.workload), 'peak_source': peak_src,
+                'algorithmic_bytes_per_agent_step': bytes_per_agent_step, 'lookups_per_agent_step': L,
+                'bytes_formula': '8*L + 4*B + 144 (fp64 DT element, fp32 range out)',
+                'kernel_ms': {'k_dynamics': kms[0], 'k_raymarch': kms[1], 'k_finalize': kms[2]},
+                'raymarch_share_of_step': kms[1] / max(kms.sum(), 1e-12),
+                'note': 'the 20.5 MB DT table is L2/L1-resident, so real DRAM traffic is far below the '
+                        'algorithmic bytes; see profiles/ for ncu DRAM and L2 throughput'}
+
+    # ---- end to end through the host-buffer API
+    Ke = min(K, 200)
+    io = sim.make_host_io()
+    host_pool = pool[:min(P, 64)].cpu().pin_memory()
+    for t in range(3):
+        io['actions'].copy_(host_pool[t % host_pool.shape[0]])
+        sim.step_host(io)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for t in range(Ke):
+        io['actions'].copy_(host_pool[t % host_pool.shape[0]])      # the caller's new actions (host->pinned)
+        sim.step_host(io)
+        sim.autoreset(wp, POSE_GAP, SEED + rank)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) * 1e-3)
+    e2e_s = reduce_max_scalar(e2e_s, dev)
+    h2d = NA * 2 * 8
+    d2h = NA * B * 4 + NA * 7 * 8 + NA * 8 + N + 2 * NA * 8
+    e2e = {'value': Ke * NA * world / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'steps': Ke, 'ms_per_step': 1e3 * e2e_s / Ke,
+           'api': 'Simulator.step_host -> C ABI f110_step_host (pinned H2D actions; step; lap logic; D2H scans+state+collisions+done+laps; sync)'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_rollout_rate(args.workload, args.cpu_seconds)
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
+               'lookups_per_agent_step': r['lookups_per_agent_step']}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+                'ms_per_step': dev_ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'description': w['desc'], 'map': 'example_map (1600x1600, 0.0625 m)',
+                           'num_envs_per_gpu': N, 'num_agents': A, 'num_beams': B, 'integrator': 'RK4', 'timestep': 0.01,
+                           'scan_noise': 'off', 'actions': 'steer~U[-0.4189,0.4189], speed~U[0,8] i.i.d. per tick, pregenerated in HBM',
+                           'auto_reset': 'ego collision -> hashed start pose on the raceline (in the timed tick)',
+                           'parallelism': 'env-sharded x%d, no collective' % world,
+                           'l2': 'flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)',
+                           'timing': 'sum of per-step CUDA-event times on the launch stream, max over ranks'},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_per_step * K, 'roofline': roofline,
+                'cpu_baseline': cpu,
+                'wall_ms_per_step_incl_flush': 1e3 * wall / K,
+                'step_ms_percentiles': {'p5': float(np.percentile(step_ms, 5)), 'p50': float(np.percentile(step_ms, 50)),
+                                        'p95': float(np.percentile(step_ms, 95))}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=500)
+    ap.add_argument('--warmup', type=int, default=50)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,726 @@
+// f110_b200.cu — kernels and C ABI of libf110_b200.so (see include/f110_b200.h).
+//
+// One tick (reference base_classes.py:553-612 Simulator.step) = three launches on the caller's stream:
+//   k_dynamics   thread per agent   steer FIFO, pid, RK4/Euler, yaw wrap, scan pose, pose snapshot
+//   k_raymarch   thread per beam    LUT heading, sphere tracing on the DT grid, fused iTTC predicate,
+//                                   optional seeded noise, fp32 range out (the roofline kernel)
+//   k_finalize   warp per agent     GJK vs. the other agents of the env, wall-hit state zeroing,
+//                                   opponent ray-cast inside the blocked-view window, collisions obs
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (no FMA contraction).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/f110_b200.h"
+#include "collision.cuh"
+#include "dynamics.cuh"
+#include "lidar.cuh"
+
+namespace f110 {
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+    return F110_ERR_CUDA;
+}
+#define CUDA_TRY(call)                                                   \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);            \
+    } while (0)
+#define LAUNCH_CHECK(name)                                               \
+    do {                                                                 \
+        cudaError_t e__ = cudaGetLastError();                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, name);             \
+    } while (0)
+
+static MapView make_view(const f110_map *m) {
+    MapView v;
+    v.dt = m->dt; v.sines = m->sines; v.cosines = m->cosines;
+    v.orig_x = m->orig_x; v.orig_y = m->orig_y; v.orig_c = m->orig_c; v.orig_s = m->orig_s;
+    v.resolution = m->resolution; v.inv_resolution = 1.0 / m->resolution;
+    v.x_max = m->width * m->resolution;    // `width * resolution` (laser_models.py:79)
+    v.y_max = m->height * m->resolution;
+    v.eps = m->eps; v.max_range = m->max_range; v.dt_oob = m->dt_oob;
+    v.theta_dis = m->theta_dis; v.theta_dis_f = (double)m->theta_dis;
+    v.height = m->height; v.width = m->width;
+    return v;
+}
+
+struct BeamView {
+    const double *__restrict__ scan_angles;
+    const double *__restrict__ cosines;
+    const double *__restrict__ side_distances;
+    double fov, angle_increment, theta_index_increment;
+    int32_t num_beams;
+};
+static BeamView make_view(const f110_beams *b) {
+    BeamView v;
+    v.scan_angles = b->scan_angles; v.cosines = b->cosines; v.side_distances = b->side_distances;
+    v.fov = b->fov; v.angle_increment = b->angle_increment; v.theta_index_increment = b->theta_index_increment;
+    v.num_beams = b->num_beams;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------ k_dynamics
+__global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
+                                                  double theta_dis_f) {
+    const int NA = s.num_envs * s.num_agents;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= NA) return;
+    const double *p = s.params + (size_t)(a % s.num_agents) * F110_NPARAM;
+    double st[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) st[k] = s.state[(size_t)k * NA + a];
+    // steering delay FIFO (base_classes.py:270-278): depth 2, zeros until two commands are queued
+    const double raw_steer = actions[2 * (size_t)a], speed = actions[2 * (size_t)a + 1];
+    int cnt = s.steer_cnt[a];
+    double b0 = s.steer_buf[a], b1 = s.steer_buf[(size_t)NA + a];
+    double steer = (cnt < 2) ? 0. : b1;
+    s.steer_buf[(size_t)NA + a] = b0;
+    s.steer_buf[a] = raw_steer;
+    if (cnt < 2) s.steer_cnt[a] = cnt + 1;
+
+    integrate_tick(st, steer, speed, p, s.timestep, s.integrator);
+
+#pragma unroll
+    for (int k = 0; k < 7; k++) s.state[(size_t)k * NA + a] = st[k];
+    // scan pose (base_classes.py:406-409) and the first beam's LUT index (laser_models.py:167-172)
+    double sx = st[0], sy = st[1];
+    if (s.lidar_dist != 0.0) {
+        sx = st[0] + s.lidar_dist * cos(st[4]);
+        sy = st[1] + s.lidar_dist * sin(st[4]);
+    }
+    double2 *sp = reinterpret_cast<double2 *>(s.scan_pose) + 2 * (size_t)a;
+    sp[0] = make_double2(sx, sy);
+    sp[1] = make_double2(st[4], theta_index0(st[4], fov, theta_dis_f));
+    s.agent_poses[3 * (size_t)a] = st[0];
+    s.agent_poses[3 * (size_t)a + 1] = st[1];
+    s.agent_poses[3 * (size_t)a + 2] = st[4];
+    s.wall_flag[a] = 0;
+}
+
+// ------------------------------------------------------------------------------------ k_raymarch
+// One thread per beam; a warp owns 32 consecutive beams of (mostly) one agent, so its lanes walk
+// neighbouring cells of the DT grid.  The grid is read through the read-only path: per scan the
+// ~7-8 k lookups touch only ~1.3 k distinct 32-byte sectors (measured), i.e. the working
+// set of the agents resident on an SM lives in L1 and the whole 20 MB table in L2.
+struct MarchArgs {
+    const double *__restrict__ scan_pose;   // [M][4] (x, y, yaw, theta_index0)    (STANDALONE: [M][3])
+    const double *__restrict__ vel;         // [M] longitudinal velocity for iTTC, or NULL
+    float *__restrict__ out_f32;            // [M][B] or NULL
+    double *__restrict__ out_f64;           // [M][B] or NULL
+    int32_t *__restrict__ wall_flag;        // [M] or NULL
+    unsigned long long *lookup_counter;     // [1] or NULL
+    const unsigned long long *tick_counter; // [1] or NULL (noise stream id)
+    double ttc_thresh, noise_std;
+    unsigned long long noise_seed;
+    long long total;                        // M * B
+};
+
+template <bool FAST, bool STANDALONE>
+__global__ void __launch_bounds__(256) k_raymarch(MapView m, BeamView bv, MarchArgs g) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = gid < g.total;
+    int nlook = 0;
+    if (valid) {
+        const int B = bv.num_beams;
+        const int a = (int)(gid / B);
+        const int i = (int)(gid - (long long)a * B);
+        double px, py, ti0;
+        if (STANDALONE) {
+            px = g.scan_pose[3 * (size_t)a];
+            py = g.scan_pose[3 * (size_t)a + 1];
+            ti0 = theta_index0(g.scan_pose[3 * (size_t)a + 2], bv.fov, m.theta_dis_f);
+        } else {
+            const double2 *sp = reinterpret_cast<const double2 *>(g.scan_pose) + 2 * (size_t)a;
+            const double2 xy = __ldg(sp), yt = __ldg(sp + 1);
+            px = xy.x; py = xy.y; ti0 = yt.y;
+        }
+        const int ti = beam_theta_index(ti0, i, bv.theta_index_increment, m.theta_dis_f);
+        const double s = __ldg(m.sines + ti), c = __ldg(m.cosines + ti);
+        double range = trace_ray<FAST>(m, px, py, s, c, nlook);
+        if (g.noise_std > 0.0) {
+            unsigned long long tick = g.tick_counter ? *g.tick_counter : 0ull;
+            range = range + g.noise_std * normal_sample(g.noise_seed, tick, (uint64_t)gid);
+        }
+        if (g.wall_flag) {
+            const double v = __ldg(g.vel + a);
+            if (ttc_hit(range, v, __ldg(bv.cosines + i), __ldg(bv.side_distances + i), g.ttc_thresh))
+                atomicOr(g.wall_flag + a, 1);
+        }
+        if (g.out_f32) g.out_f32[gid] = (float)range;
+        if (g.out_f64) g.out_f64[gid] = range;
+    }
+    if (g.lookup_counter) {
+        unsigned n = (unsigned)nlook;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(g.lookup_counter, (unsigned long long)n);
+    }
+}
+
+// ------------------------------------------------------------------------------------ k_finalize
+// Warp per agent (base_classes.py:536-550 check_collision, :579-589 update_scan loop).
+__global__ void __launch_bounds__(128) k_finalize(f110_sim s, BeamView bv) {
+    const int NA = s.num_envs * s.num_agents;
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= NA) return;
+    const int A = s.num_agents;
+    const int env = a / A, slot = a - env * A;
+    const int hit = s.wall_flag[a];
+    const double px = s.state[a], py = s.state[(size_t)NA + a];
+    // check_ttc zeroes state[3:] — including the yaw — before the opponent ray-cast reads it (:246-249, :225)
+    const double yaw = hit ? 0.0 : s.state[(size_t)4 * NA + a];
+    __syncwarp();
+    if (hit && lane < 4) s.state[(size_t)(3 + lane) * NA + a] = 0.0;
+
+    // GJK against the other agents of this env, lower index first (collision_multiple :184-212)
+    int col = 0, cidx = -1;
+    if (A > 1) {
+        double vme[8];
+        const double *pa = s.agent_poses + 3 * (size_t)a;
+        get_vertices(pa[0], pa[1], pa[2], s.sim_length, s.sim_width, vme);
+        for (int j = lane; j < A; j += 32) {
+            if (j == slot) continue;
+            const double *pb = s.agent_poses + 3 * (size_t)(env * A + j);
+            double vo[8];
+            get_vertices(pb[0], pb[1], pb[2], s.sim_length, s.sim_width, vo);
+            bool c = (slot < j) ? gjk_collision(vme, vo) : gjk_collision(vo, vme);
+            if (c) { col = 1; cidx = max(cidx, j); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            col |= __shfl_xor_sync(0xffffffffu, col, o);
+            cidx = max(cidx, __shfl_xor_sync(0xffffffffu, cidx, o));
+        }
+    }
+    if (lane == 0) {
+        s.collisions[a] = (col || hit) ? 1.0 : 0.0;
+        s.collision_idx[a] = cidx;
+    }
+
+    // ray_cast_agents (:206-227): opponents in ascending index, each bounded to its blocked-view window
+    if (A > 1) {
+        const double *p = s.params + (size_t)slot * F110_NPARAM;
+        const double length = p[P_LENGTH], width = p[P_WIDTH];
+        float *scan = s.scans + (size_t)a * bv.num_beams;
+        for (int j = 0; j < A; j++) {
+            if (j == slot) continue;
+            const double *pb = s.agent_poses + 3 * (size_t)(env * A + j);
+            double v[8];
+            get_vertices(pb[0], pb[1], pb[2], length, width, v);
+            int lo, hi;
+            blocked_view_indices(px, py, yaw, v, bv.scan_angles, bv.num_beams, bv.fov, bv.angle_increment, lo, hi);
+            for (int i = lo + lane; i <= hi; i += 32) {
+                double bt = yaw + bv.scan_angles[i];
+                double v3x = cos(bt + M_PI / 2.), v3y = sin(bt + M_PI / 2.);
+                double r = INFINITY;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    int e2 = (e + 1) & 3;
+                    double d = get_range(px, py, v3x, v3y, v[2 * e], v[2 * e + 1], v[2 * e2], v[2 * e2 + 1]);
+                    if (d < r) r = d;
+                }
+                float rf = (float)r;
+                if (rf < scan[i]) scan[i] = rf;
+            }
+            __syncwarp();
+        }
+    }
+    // tick counter: bumped once per f110_step by the last kernel of the tick
+    if (a == 0 && lane == 0 && s.tick_counter) *s.tick_counter += 1ull;
+}
+
+// ------------------------------------------------------------------------------------ reset kernels
+__global__ void k_reset(f110_sim s, const double *__restrict__ poses, const uint8_t *__restrict__ mask) {
+    const int NA = s.num_envs * s.num_agents;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= NA) return;
+    if (mask && !mask[a / s.num_agents]) return;
+    // RaceCar.reset base_classes.py:183-204
+#pragma unroll
+    for (int k = 0; k < 7; k++) s.state[(size_t)k * NA + a] = 0.0;
+    s.state[a] = poses[3 * (size_t)a];
+    s.state[(size_t)NA + a] = poses[3 * (size_t)a + 1];
+    s.state[(size_t)4 * NA + a] = poses[3 * (size_t)a + 2];
+    s.steer_cnt[a] = 0;
+    s.steer_buf[a] = 0.0;
+    s.steer_buf[(size_t)NA + a] = 0.0;
+    s.wall_flag[a] = 0;
+}
+
+__device__ __forceinline__ void env_counters_reset(const f110_sim &s, int env, const double *agent_pose3 /* [A][3] */) {
+    const int A = s.num_agents;
+    s.current_time[env] = 0.0;
+    for (int i = 0; i < A; i++) {
+        const size_t a = (size_t)env * A + i;
+        s.near_starts[a] = 1;
+        s.toggle_list[a] = 0.0;
+        s.start_xs[a] = agent_pose3[3 * i];
+        s.start_ys[a] = agent_pose3[3 * i + 1];
+        s.start_thetas[a] = agent_pose3[3 * i + 2];
+    }
+    // f110_env.py:331 start_rot from the ego's start heading
+    const double th = -agent_pose3[3 * s.ego_idx + 2];
+    double *R = s.start_rot + 4 * (size_t)env;
+    R[0] = cos(th); R[1] = -sin(th); R[2] = sin(th); R[3] = cos(th);
+    if (s.done) s.done[env] = 0;
+}
+
+__global__ void k_env_reset(f110_sim s, const double *__restrict__ poses, const uint8_t *__restrict__ mask) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= s.num_envs) return;
+    if (mask && !mask[env]) return;
+    env_counters_reset(s, env, poses + 3 * (size_t)env * s.num_agents);
+}
+
+// f110_env.py:294-302 + _check_done :204-246, thread per env
+__global__ void k_env_post_step(f110_sim s) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= s.num_envs) return;
+    const int A = s.num_agents, NA = s.num_envs * s.num_agents;
+    const double left_t = 2, right_t = 2;
+    const double now = s.current_time[env] + s.timestep;
+    s.current_time[env] = now;
+    const double *R = s.start_rot + 4 * (size_t)env;
+    bool all_done = true;
+    for (int i = 0; i < A; i++) {
+        const size_t a = (size_t)env * A + i;
+        double px = s.state[a] - s.start_xs[a];
+        double py = s.state[(size_t)NA + a] - s.start_ys[a];
+        double dx = R[0] * px + R[1] * py;
+        double ty = R[2] * px + R[3] * py;
+        if (ty > left_t) ty -= left_t;
+        else if (ty < -right_t) ty = -right_t - ty;
+        else ty = 0;
+        double dist2 = dx * dx + ty * ty;
+        bool close = dist2 <= 0.1;
+        int near = s.near_starts[a];
+        double tog = s.toggle_list[a];
+        if (close && !near) { near = 1; tog += 1; }
+        else if (!close && near) { near = 0; tog += 1; }
+        s.near_starts[a] = near;
+        s.toggle_list[a] = tog;
+        s.lap_counts[a] = floor(tog / 2);
+        if (tog < 4) s.lap_times[a] = now;
+        bool cp = tog >= 4;
+        if (s.checkpoint_done) s.checkpoint_done[a] = cp ? 1 : 0;
+        all_done = all_done && cp;
+    }
+    s.done[env] = ((s.collisions[(size_t)env * A + s.ego_idx] != 0.0) || all_done) ? 1 : 0;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_autoreset(f110_sim s, const double *__restrict__ start_poses, int num_start, int pose_gap,
+                            uint64_t seed, const unsigned long long *tick_counter, uint64_t tick_host) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= s.num_envs) return;
+    const int A = s.num_agents, NA = s.num_envs * s.num_agents;
+    if (s.collisions[(size_t)env * A + s.ego_idx] == 0.0) return;
+    const uint64_t tick = tick_counter ? (uint64_t)*tick_counter : tick_host;
+    uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (tick + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(env + 1));
+    int k = (int)((double)(h >> 11) * (1.0 / 9007199254740992.0) * num_start);
+    if (k >= num_start) k = num_start - 1;
+    double pose3[3 * 32];
+    for (int i = 0; i < A; i++) {
+        int kk = ((k - pose_gap * i) % num_start + num_start) % num_start;
+        const size_t a = (size_t)env * A + i;
+        const double x = start_poses[3 * kk], y = start_poses[3 * kk + 1], th = start_poses[3 * kk + 2];
+        if (i < 32) { pose3[3 * i] = x; pose3[3 * i + 1] = y; pose3[3 * i + 2] = th; }
+#pragma unroll
+        for (int q = 0; q < 7; q++) s.state[(size_t)q * NA + a] = 0.0;
+        s.state[a] = x;
+        s.state[(size_t)NA + a] = y;
+        s.state[(size_t)4 * NA + a] = th;
+        s.steer_cnt[a] = 0;
+        s.steer_buf[a] = 0.0;
+        s.steer_buf[(size_t)NA + a] = 0.0;
+        s.wall_flag[a] = 0;
+    }
+    if (s.current_time && A <= 32) env_counters_reset(s, env, pose3);
+}
+
+// ------------------------------------------------------------------------------------ standalone kernels
+__global__ void k_rhs(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ p,
+                      int M, double *__restrict__ f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double xs[7], fs[7];
+    for (int k = 0; k < 7; k++) xs[k] = x[7 * (size_t)i + k];
+    vehicle_dynamics_st(xs, u[2 * (size_t)i], u[2 * (size_t)i + 1], p, fs);
+    for (int k = 0; k < 7; k++) f[7 * (size_t)i + k] = fs[k];
+}
+
+__global__ void k_pid(const double *__restrict__ in, const double *__restrict__ p, int M, double *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double accl, sv;
+    pid(in[4 * (size_t)i], in[4 * (size_t)i + 1], in[4 * (size_t)i + 2], in[4 * (size_t)i + 3], p[P_SVMAX],
+        p[P_AMAX], p[P_VMAX], p[P_VMIN], accl, sv);
+    out[2 * (size_t)i] = accl;
+    out[2 * (size_t)i + 1] = sv;
+}
+
+__global__ void k_vertices(const double *__restrict__ poses, double length, double width, int M,
+                           double *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double v[8];
+    get_vertices(poses[3 * (size_t)i], poses[3 * (size_t)i + 1], poses[3 * (size_t)i + 2], length, width, v);
+    for (int k = 0; k < 8; k++) out[8 * (size_t)i + k] = v[k];
+}
+
+__global__ void k_gjk(const double *__restrict__ va, const double *__restrict__ vb, int M, int32_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double a[8], b[8];
+    for (int k = 0; k < 8; k++) { a[k] = va[8 * (size_t)i + k]; b[k] = vb[8 * (size_t)i + k]; }
+    out[i] = gjk_collision(a, b) ? 1 : 0;
+}
+
+__global__ void k_gjk_multiple(const double *__restrict__ verts, int M, int n, double *__restrict__ collisions,
+                               double *__restrict__ collision_idx) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M) return;
+    const double *V = verts + (size_t)e * n * 8;
+    for (int i = 0; i < n; i++) { collisions[(size_t)e * n + i] = 0.; collision_idx[(size_t)e * n + i] = -1.; }
+    for (int i = 0; i < n - 1; i++)
+        for (int j = i + 1; j < n; j++) {
+            double a[8], b[8];
+            for (int k = 0; k < 8; k++) { a[k] = V[8 * i + k]; b[k] = V[8 * j + k]; }
+            if (gjk_collision(a, b)) {
+                collisions[(size_t)e * n + i] = 1.; collisions[(size_t)e * n + j] = 1.;
+                collision_idx[(size_t)e * n + i] = j; collision_idx[(size_t)e * n + j] = i;
+            }
+        }
+}
+
+__global__ void k_check_ttc(BeamView bv, const double *__restrict__ scans, const double *__restrict__ vel,
+                            double thresh, int M, int32_t *__restrict__ out) {
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= M) return;
+    int hit = 0;
+    for (int i = lane; i < bv.num_beams; i += 32)
+        hit |= ttc_hit(scans[(size_t)a * bv.num_beams + i], vel[a], bv.cosines[i], bv.side_distances[i], thresh) ? 1 : 0;
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) out[a] = hit ? 1 : 0;
+}
+
+__global__ void k_ray_cast(BeamView bv, const double *__restrict__ poses, const double *__restrict__ opp, int M,
+                           float *__restrict__ scans, int32_t *__restrict__ window) {
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= M) return;
+    const double px = poses[3 * (size_t)a], py = poses[3 * (size_t)a + 1], yaw = poses[3 * (size_t)a + 2];
+    double v[8];
+    for (int k = 0; k < 8; k++) v[k] = opp[8 * (size_t)a + k];
+    int lo, hi;
+    blocked_view_indices(px, py, yaw, v, bv.scan_angles, bv.num_beams, bv.fov, bv.angle_increment, lo, hi);
+    if (window && lane == 0) { window[2 * a] = lo; window[2 * a + 1] = hi; }
+    float *scan = scans + (size_t)a * bv.num_beams;
+    for (int i = lo + lane; i <= hi; i += 32) {
+        double bt = yaw + bv.scan_angles[i];
+        double v3x = cos(bt + M_PI / 2.), v3y = sin(bt + M_PI / 2.);
+        double r = INFINITY;
+        for (int e = 0; e < 4; e++) {
+            int e2 = (e + 1) & 3;
+            double d = get_range(px, py, v3x, v3y, v[2 * e], v[2 * e + 1], v[2 * e2], v[2 * e2 + 1]);
+            if (d < r) r = d;
+        }
+        float rf = (float)r;
+        if (rf < scan[i]) scan[i] = rf;
+    }
+}
+
+__global__ void k_scan_noise(float *__restrict__ scans, long long count, double std_dev, uint64_t seed,
+                             uint64_t offset) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    scans[i] = (float)((double)scans[i] + std_dev * normal_sample(seed, 0xFFFFFFFFull, offset + (uint64_t)i));
+}
+
+static int check_sim(const f110_sim *s) {
+    if (!s) return F110_ERR_INVALID;
+    if (s->num_envs <= 0 || s->num_agents <= 0) return F110_ERR_INVALID;
+    if (s->integrator != 1 && s->integrator != 2) return F110_ERR_INTEGRATOR;
+    if (!s->params || !s->state || !s->steer_buf || !s->steer_cnt || !s->scan_pose || !s->agent_poses ||
+        !s->scans || !s->wall_flag || !s->collisions || !s->collision_idx)
+        return F110_ERR_INVALID;
+    return F110_OK;
+}
+static int check_map(const f110_map *m) {
+    if (!m) return F110_ERR_INVALID;
+    if (!m->dt || m->height <= 0 || m->width <= 0) return F110_ERR_NO_MAP;
+    if (!m->sines || !m->cosines || m->theta_dis <= 0 || !(m->resolution > 0)) return F110_ERR_INVALID;
+    return F110_OK;
+}
+static int check_beams(const f110_beams *b) {
+    if (!b || b->num_beams <= 1 || !b->scan_angles || !b->cosines || !b->side_distances) return F110_ERR_INVALID;
+    return F110_OK;
+}
+
+static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArgs &g, bool fast, bool standalone,
+                           cudaStream_t st) {
+    const int threads = 256;
+    const long long blocks = (g.total + threads - 1) / threads;
+    if (blocks <= 0 || blocks > 0x7fffffffll) return F110_ERR_INVALID;
+    if (standalone) {
+        if (fast) k_raymarch<true, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+        else k_raymarch<false, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+    } else {
+        if (fast) k_raymarch<true, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+        else k_raymarch<false, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+    }
+    LAUNCH_CHECK("k_raymarch");
+    return F110_OK;
+}
+
+}  // namespace f110
+
+using namespace f110;
+
+// ================================================================================== C ABI
+extern "C" {
+
+int f110_abi_version(void) { return F110_ABI_VERSION; }
+
+const char *f110_status_string(int status) {
+    switch (status) {
+        case F110_OK: return "ok";
+        case F110_ERR_INVALID: return "invalid argument";
+        case F110_ERR_NO_MAP: return "Map is not set for scan simulator.";
+        case F110_ERR_CUDA: return "CUDA runtime error";
+        case F110_ERR_INTEGRATOR: return "Invalid Integrator Specified. Please choose RK4 or Euler";
+        case F110_ERR_POSE_COUNT: return "Number of poses for reset does not match number of agents.";
+        case F110_ERR_AGENT_INDEX: return "Index given is out of bounds for list of agents.";
+        default: return "unknown status";
+    }
+}
+
+const char *f110_last_cuda_error(void) { return g_cuda_err; }
+
+static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions,
+                     cudaStream_t st, cudaEvent_t *ev /* NULL or [4] */) {
+    int rc;
+    if ((rc = check_sim(sim)) || (rc = check_map(map)) || (rc = check_beams(beams))) return rc;
+    if (!actions) return F110_ERR_INVALID;
+    const int NA = sim->num_envs * sim->num_agents;
+    const MapView mv = make_view(map);
+    const BeamView bv = make_view(beams);
+
+    if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
+    k_dynamics<<<(NA + 127) / 128, 128, 0, st>>>(*sim, actions, beams->fov, (double)map->theta_dis);
+    LAUNCH_CHECK("k_dynamics");
+    if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
+
+    MarchArgs g;
+    g.scan_pose = sim->scan_pose;
+    g.vel = sim->state + (size_t)3 * NA;
+    g.out_f32 = sim->scans;
+    g.out_f64 = nullptr;
+    g.wall_flag = sim->wall_flag;
+    g.lookup_counter = sim->lookup_counter;
+    g.tick_counter = sim->tick_counter;
+    g.ttc_thresh = sim->ttc_thresh;
+    g.noise_std = sim->noise_std;
+    g.noise_seed = sim->noise_seed;
+    g.total = (long long)NA * beams->num_beams;
+    if ((rc = launch_raymarch(mv, bv, g, map->fast_path != 0, false, st))) return rc;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
+
+    k_finalize<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv);
+    LAUNCH_CHECK("k_finalize");
+    if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
+    return F110_OK;
+}
+
+int f110_step(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions,
+              void *stream) {
+    return step_impl(sim, map, beams, actions, (cudaStream_t)stream, nullptr);
+}
+
+int f110_step_profile(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions,
+                      float *kernel_ms /* host [3] */, void *stream) {
+    if (!kernel_ms) return F110_ERR_INVALID;
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+    int rc = step_impl(sim, map, beams, actions, (cudaStream_t)stream, ev);
+    if (rc == F110_OK) {
+        cudaError_t e = cudaEventSynchronize(ev[3]);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
+        for (int i = 0; i < 3 && rc == F110_OK; i++) {
+            e = cudaEventElapsedTime(&kernel_ms[i], ev[i], ev[i + 1]);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventElapsedTime");
+        }
+    }
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+int f110_reset(const f110_sim *sim, const double *poses, const uint8_t *env_mask, void *stream) {
+    int rc;
+    if ((rc = check_sim(sim))) return rc;
+    if (!poses) return F110_ERR_INVALID;
+    const int NA = sim->num_envs * sim->num_agents;
+    k_reset<<<(NA + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sim, poses, env_mask);
+    LAUNCH_CHECK("k_reset");
+    return F110_OK;
+}
+
+static int check_env_arrays(const f110_sim *s) {
+    if (!s->current_time || !s->lap_times || !s->lap_counts || !s->toggle_list || !s->near_starts ||
+        !s->start_xs || !s->start_ys || !s->start_thetas || !s->start_rot || !s->done)
+        return F110_ERR_INVALID;
+    if (s->ego_idx < 0 || s->ego_idx >= s->num_agents) return F110_ERR_AGENT_INDEX;
+    return F110_OK;
+}
+
+int f110_env_reset(const f110_sim *sim, const double *poses, const uint8_t *env_mask, void *stream) {
+    int rc;
+    if ((rc = check_sim(sim)) || (rc = check_env_arrays(sim))) return rc;
+    if (!poses) return F110_ERR_INVALID;
+    k_env_reset<<<(sim->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sim, poses, env_mask);
+    LAUNCH_CHECK("k_env_reset");
+    return F110_OK;
+}
+
+int f110_env_post_step(const f110_sim *sim, void *stream) {
+    int rc;
+    if ((rc = check_sim(sim)) || (rc = check_env_arrays(sim))) return rc;
+    k_env_post_step<<<(sim->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sim);
+    LAUNCH_CHECK("k_env_post_step");
+    return F110_OK;
+}
+
+int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_start, int32_t pose_gap,
+                   uint64_t seed, uint64_t tick, void *stream) {
+    int rc;
+    if ((rc = check_sim(sim))) return rc;
+    if (!start_poses || num_start <= 0) return F110_ERR_INVALID;
+    if (sim->ego_idx < 0 || sim->ego_idx >= sim->num_agents) return F110_ERR_AGENT_INDEX;
+    k_autoreset<<<(sim->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sim, start_poses, num_start, pose_gap,
+                                                                               seed, sim->tick_counter, tick);
+    LAUNCH_CHECK("k_autoreset");
+    return F110_OK;
+}
+
+int f110_step_host(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions_host,
+                   double *actions_dev_scratch, const f110_host_obs *out, void *stream) {
+    int rc;
+    if ((rc = check_sim(sim))) return rc;
+    if (!actions_host || !actions_dev_scratch || !out) return F110_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t NA = (size_t)sim->num_envs * sim->num_agents;
+    CUDA_TRY(cudaMemcpyAsync(actions_dev_scratch, actions_host, NA * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = f110_step(sim, map, beams, actions_dev_scratch, stream))) return rc;
+    const bool env_level = sim->current_time && sim->done;
+    if (env_level && (rc = f110_env_post_step(sim, stream))) return rc;
+    if (out->scans)
+        CUDA_TRY(cudaMemcpyAsync(out->scans, sim->scans, NA * beams->num_beams * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out->state)
+        CUDA_TRY(cudaMemcpyAsync(out->state, sim->state, NA * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out->collisions)
+        CUDA_TRY(cudaMemcpyAsync(out->collisions, sim->collisions, NA * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (env_level) {
+        if (out->done)
+            CUDA_TRY(cudaMemcpyAsync(out->done, sim->done, (size_t)sim->num_envs, cudaMemcpyDeviceToHost, st));
+        if (out->lap_times)
+            CUDA_TRY(cudaMemcpyAsync(out->lap_times, sim->lap_times, NA * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (out->lap_counts)
+            CUDA_TRY(cudaMemcpyAsync(out->lap_counts, sim->lap_counts, NA * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return F110_OK;
+}
+
+int f110_scan(const f110_map *map, const f110_beams *beams, const double *poses, int32_t M, float *out_f32,
+              double *out_f64, unsigned long long *lookup_counter, void *stream) {
+    int rc;
+    if ((rc = check_map(map)) || (rc = check_beams(beams))) return rc;
+    if (!poses || M <= 0 || (!out_f32 && !out_f64)) return F110_ERR_INVALID;
+    MarchArgs g;
+    memset(&g, 0, sizeof(g));
+    g.scan_pose = poses;
+    g.out_f32 = out_f32;
+    g.out_f64 = out_f64;
+    g.lookup_counter = lookup_counter;
+    g.total = (long long)M * beams->num_beams;
+    return launch_raymarch(make_view(map), make_view(beams), g, map->fast_path != 0, true, (cudaStream_t)stream);
+}
+
+int f110_vehicle_dynamics_st(const double *x, const double *u, const double *params, int32_t M, double *f, void *stream) {
+    if (!x || !u || !params || !f || M <= 0) return F110_ERR_INVALID;
+    k_rhs<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, u, params, M, f);
+    LAUNCH_CHECK("k_rhs");
+    return F110_OK;
+}
+
+int f110_pid(const double *in, const double *params, int32_t M, double *out, void *stream) {
+    if (!in || !params || !out || M <= 0) return F110_ERR_INVALID;
+    k_pid<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, params, M, out);
+    LAUNCH_CHECK("k_pid");
+    return F110_OK;
+}
+
+int f110_get_vertices(const double *poses, double length, double width, int32_t M, double *out, void *stream) {
+    if (!poses || !out || M <= 0) return F110_ERR_INVALID;
+    k_vertices<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(poses, length, width, M, out);
+    LAUNCH_CHECK("k_vertices");
+    return F110_OK;
+}
+
+int f110_collision(const double *va, const double *vb, int32_t M, int32_t *out, void *stream) {
+    if (!va || !vb || !out || M <= 0) return F110_ERR_INVALID;
+    k_gjk<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(va, vb, M, out);
+    LAUNCH_CHECK("k_gjk");
+    return F110_OK;
+}
+
+int f110_collision_multiple(const double *verts, int32_t M, int32_t n, double *collisions, double *collision_idx,
+                            void *stream) {
+    if (!verts || !collisions || !collision_idx || M <= 0 || n <= 0) return F110_ERR_INVALID;
+    k_gjk_multiple<<<(M + 63) / 64, 64, 0, (cudaStream_t)stream>>>(verts, M, n, collisions, collision_idx);
+    LAUNCH_CHECK("k_gjk_multiple");
+    return F110_OK;
+}
+
+int f110_check_ttc(const f110_beams *beams, const double *scans, const double *vel, double ttc_thresh, int32_t M,
+                   int32_t *out, void *stream) {
+    int rc;
+    if ((rc = check_beams(beams))) return rc;
+    if (!scans || !vel || !out || M <= 0) return F110_ERR_INVALID;
+    k_check_ttc<<<((long long)M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_view(beams), scans, vel,
+                                                                                   ttc_thresh, M, out);
+    LAUNCH_CHECK("k_check_ttc");
+    return F110_OK;
+}
+
+int f110_ray_cast(const f110_beams *beams, const double *poses, const double *opp_vertices, int32_t M, float *scans,
+                  int32_t *window, void *stream) {
+    int rc;
+    if ((rc = check_beams(beams))) return rc;
+    if (!poses || !opp_vertices || !scans || M <= 0) return F110_ERR_INVALID;
+    k_ray_cast<<<((long long)M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_view(beams), poses, opp_vertices,
+                                                                                  M, scans, window);
+    LAUNCH_CHECK("k_ray_cast");
+    return F110_OK;
+}
+
+int f110_scan_noise(float *scans, int64_t count, double std_dev, uint64_t seed, uint64_t offset, void *stream) {
+    if (!scans || count <= 0) return F110_ERR_INVALID;
+    k_scan_noise<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(scans, count, std_dev, seed, offset);
+    LAUNCH_CHECK("k_scan_noise");
+    return F110_OK;
+}
+
+}  // extern "C"

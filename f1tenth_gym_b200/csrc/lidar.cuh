@@ -1,0 +1,189 @@
+// lidar.cuh — sphere-tracing ray-march on the distance-transform grid, iTTC predicate and the
+// opponent ray-cast, fp64.
+//
+// Behavioural spec: reference gym/f110_gym/envs/laser_models.py:55-346.  Compiled with -fmad=false
+// (`x += d*c` is two roundings in the reference; SURVEY.md 7.1 shows fp32 or FMA-contracted
+// positions flip `int(x/res)` cells and break 1e-4 parity).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+namespace f110 {
+
+struct MapView {
+    const double *__restrict__ dt;
+    const double *__restrict__ sines;
+    const double *__restrict__ cosines;
+    double orig_x, orig_y, orig_c, orig_s, resolution, inv_resolution, x_max, y_max;
+    double eps, max_range, dt_oob, theta_dis_f;
+    int32_t height, width, theta_dis;
+};
+
+// laser_models.py:55-104 xy_2_rc + distance_transform.
+// FAST: resolution is a power of two and the origin is unrotated, so x_rot == x - orig_x exactly,
+// x_rot/res == x_rot*inv_res exactly, and the four fp64 bounds tests collapse to two unsigned integer
+// compares on floor() of the scaled coordinate.  Off-map reads dt[-1,-1] (numba negative-index wrap).
+template <bool FAST>
+__device__ __forceinline__ double dt_lookup(const MapView &m, double x, double y) {
+    if (FAST) {
+        double tx = (x - m.orig_x) * m.inv_resolution;
+        double ty = (y - m.orig_y) * m.inv_resolution;
+        int c = __double2int_rd(tx);
+        int r = __double2int_rd(ty);
+        bool inb = ((unsigned)c < (unsigned)m.width) && ((unsigned)r < (unsigned)m.height);
+        return inb ? __ldg(m.dt + (size_t)r * (size_t)m.width + (size_t)c) : m.dt_oob;
+    } else {
+        double x_trans = x - m.orig_x;
+        double y_trans = y - m.orig_y;
+        double x_rot = x_trans * m.orig_c + y_trans * m.orig_s;
+        double y_rot = -x_trans * m.orig_s + y_trans * m.orig_c;
+        if (x_rot < 0 || x_rot >= m.x_max || y_rot < 0 || y_rot >= m.y_max) return m.dt_oob;
+        int c = (int)(x_rot / m.resolution);
+        int r = (int)(y_rot / m.resolution);
+        return __ldg(m.dt + (size_t)r * (size_t)m.width + (size_t)c);
+    }
+}
+
+// laser_models.py:106-146 trace_ray.  Returns the clamped range; nlook gets the number of DT lookups.
+template <bool FAST>
+__device__ __forceinline__ double trace_ray(const MapView &m, double x, double y, double s, double c,
+                                            int &nlook) {
+    double d = dt_lookup<FAST>(m, x, y);
+    double total = d;
+    int n = 1;
+    while (d > m.eps && total <= m.max_range) {
+        x = x + d * c;
+        y = y + d * s;
+        d = dt_lookup<FAST>(m, x, y);
+        total = total + d;
+        n++;
+    }
+    nlook = n;
+    return (total > m.max_range) ? m.max_range : total;
+}
+
+// laser_models.py:167-172: first beam's LUT index from the scan pose yaw.
+__device__ __forceinline__ double theta_index0(double yaw, double fov, double theta_dis_f) {
+    double ti = theta_dis_f * (yaw - fov / 2.) / (2. * M_PI);
+    ti = fmod(ti, theta_dis_f);
+    while (ti < 0) ti += theta_dis_f;
+    return ti;
+}
+
+// laser_models.py:175-184: the reference walks theta_index sequentially (`+= inc`, wrap at theta_dis).
+// Per-lane closed form ti0 + i*inc (mod theta_dis); the sequential fp64 value differs from it by
+// < 1e-9, so int() can only disagree when the fractional part is within 1e-6 of an integer — in that
+// (2e-6-probability) case the exact sequential recurrence is replayed for this beam.
+__device__ __forceinline__ int beam_theta_index(double ti0, int i, double inc, double theta_dis_f) {
+    double v = ti0 + (double)i * inc;
+    v = v - theta_dis_f * floor(v / theta_dis_f);
+    double fl = floor(v);
+    double fr = v - fl;
+    if (fr < 1e-6 || fr > 1.0 - 1e-6 || v >= theta_dis_f) {
+        double t = ti0;
+        for (int k = 0; k < i; k++) {
+            t += inc;
+            while (t >= theta_dis_f) t -= theta_dis_f;
+        }
+        return (int)t;
+    }
+    return (int)fl;
+}
+
+// laser_models.py:188-217 check_ttc_jit, one beam (error_model='numpy': x/0 -> inf/nan, compares false)
+__device__ __forceinline__ bool ttc_hit(double range, double vel, double cos_i, double side_i, double thresh) {
+    if (vel == 0.0) return false;
+    double proj_vel = vel * cos_i;
+    double ttc = (range - side_i) / proj_vel;
+    return (ttc < thresh) && (ttc >= 0.0);
+}
+
+__device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) { return ax * by - ay * bx; }
+
+// laser_models.py:249-280 get_range, with (v3x, v3y) = (cos, sin)(beam_theta + pi/2) hoisted per beam
+__device__ __forceinline__ double get_range(double ox, double oy, double v3x, double v3y, double vax,
+                                            double vay, double vbx, double vby) {
+    double v1x = ox - vax, v1y = oy - vay;
+    double v2x = vbx - vax, v2y = vby - vay;
+    double denom = v2x * v3x + v2y * v3y;
+    double distance = INFINITY;
+    if (fabs(denom) > 0.0) {
+        double d1 = cross2(v2x, v2y, v1x, v1y) / denom;
+        double d2 = (v1x * v3x + v1y * v3y) / denom;
+        if (d1 >= 0.0 && d2 >= 0.0 && d2 <= 1.0) distance = d1;
+    } else {
+        // are_collinear(o, va, vb) :232-247
+        double bax = vax - ox, bay = vay - oy, cax = ox - vbx, cay = oy - vby;
+        if (fabs(cross2(bax, bay, cax, cay)) < 1e-8) {
+            double da = sqrt((vax - ox) * (vax - ox) + (vay - oy) * (vay - oy));
+            double db = sqrt((vbx - ox) * (vbx - ox) + (vby - oy) * (vby - oy));
+            distance = da < db ? da : db;
+        }
+    }
+    return distance;
+}
+
+// np.argmin(np.abs(scan_angles - a)) (first minimum).  scan_angles is strictly increasing, so
+// |scan_angles[i] - a| is convex in i: evaluate the table around the analytic estimate.
+__device__ __forceinline__ int nearest_beam(const double *__restrict__ scan_angles, int num_beams,
+                                            double fov, double angle_increment, double a) {
+    double est = (a + fov / 2.) / angle_increment;
+    int i0;
+    if (!(est > 0.0)) i0 = 0;
+    else if (est >= (double)(num_beams - 1)) i0 = num_beams - 1;
+    else i0 = (int)est;
+    int lo = max(i0 - 2, 0), hi = min(i0 + 3, num_beams - 1);
+    int best = lo;
+    double bv = fabs(scan_angles[lo] - a);
+    for (int i = lo + 1; i <= hi; i++) {
+        double v = fabs(scan_angles[i] - a);
+        if (v < bv) { bv = v; best = i; }
+    }
+    return best;
+}
+
+// laser_models.py:282-315 get_blocked_view_indices
+__device__ __forceinline__ void blocked_view_indices(double px, double py, double yaw, const double v[8],
+                                                     const double *__restrict__ scan_angles, int num_beams,
+                                                     double fov, double angle_increment, int &min_ind,
+                                                     int &max_ind) {
+    double ego_a = atan2(sin(yaw), cos(yaw));
+    int lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double vx = v[2 * i] - px, vy = v[2 * i + 1] - py;
+        double norm = sqrt(vx * vx + vy * vy);
+        double ux = vx / norm, uy = vy / norm;
+        double angle = ego_a - atan2(uy, ux);
+        if (angle > M_PI) angle = angle - 2 * M_PI;
+        else if (angle < -M_PI) angle = angle + 2 * M_PI;
+        int ind = nearest_beam(scan_angles, num_beams, fov, angle_increment, -angle);
+        if (i == 0) { lo = hi = ind; }
+        else { lo = min(lo, ind); hi = max(hi, ind); }
+    }
+    min_ind = lo;
+    max_ind = hi;
+}
+
+// ---- counter-based RNG for the optional scan noise (laser_models.py:450-452) -------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// one standard normal per (seed, stream, index) via Box-Muller on two 32-bit uniforms
+__device__ __forceinline__ double normal_sample(uint64_t seed, uint64_t stream, uint64_t index) {
+    uint32_t c[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)stream, (uint32_t)(stream >> 32) };
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    double u1 = ((double)c[0] + 1.0) * (1.0 / 4294967296.0);   // (0, 1]
+    double u2 = (double)c[1] * (1.0 / 4294967296.0);           // [0, 1)
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+}  // namespace f110

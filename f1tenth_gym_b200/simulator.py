@@ -1,0 +1,319 @@
+"""Batched Simulator: the host-side mirror of reference base_classes.py (Simulator / RaceCar) for
+N independent environments x A agents stepped in lockstep by the CUDA path.
+
+Mirrors the reference interface for this path — same constructor arguments, method names, argument
+meaning and error behaviour:
+    Simulator(params, num_agents, seed, time_step=0.01, ego_idx=0, integrator=Integrator.RK4,
+              lidar_dist=0.0)                                   base_classes.py:465-497
+    .set_map(map_path, map_ext)                                 :499-511
+    .update_params(params, agent_idx=-1)   IndexError           :514-534
+    .reset(poses)                           ValueError           :614-630
+    .step(control_inputs) -> observations dict                  :553-612
+plus the batch extensions `num_envs`, `num_beams`, `fov`, `device`, `noise_std`.
+
+PyTorch is used only as the device-memory allocator and stream provider; all compute goes through
+the C ABI in libf110_b200.so (include/f110_b200.h).  There is no CPU fallback.
+"""
+import ctypes as C
+from enum import Enum
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import maps as hostmaps
+
+
+class Integrator(Enum):     # base_classes.py:40-42
+    RK4 = 1
+    Euler = 2
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DeviceMap(object):
+    """ScanSimulator2D state (laser_models.py:348-427) resident in HBM: fp64 DT grid + angle LUTs."""
+
+    def __init__(self, host_map, device, theta_dis=2000, eps=0.0001, max_range=30.0):
+        self.host = host_map
+        self.device = device
+        self.theta_dis = theta_dis
+        sines, cosines = hostmaps.angle_lut(theta_dis)
+        self.dt = torch.from_numpy(host_map.dt).to(device)
+        self.sines = torch.from_numpy(sines).to(device)
+        self.cosines = torch.from_numpy(cosines).to(device)
+        self.c = nat.F110Map(host_map.height, host_map.width, host_map.resolution, host_map.orig_x,
+                             host_map.orig_y, host_map.orig_c, host_map.orig_s, eps, max_range, theta_dis,
+                             host_map.fast_path, host_map.dt_oob, nat.ptr(self.dt), nat.ptr(self.sines),
+                             nat.ptr(self.cosines))
+
+    @classmethod
+    def from_yaml(cls, map_path, map_ext, device, **kw):
+        return cls(hostmaps.load_map(map_path, map_ext), device, **kw)
+
+
+class DeviceBeams(object):
+    """Per-beam tables of RaceCar.__init__ (base_classes.py:122-158) in HBM."""
+
+    def __init__(self, num_beams, fov, params, device, theta_dis=2000):
+        self.num_beams, self.fov = num_beams, fov
+        sa, co, sd = hostmaps.beam_tables(num_beams, fov, params)
+        self.scan_angles = torch.from_numpy(sa).to(device)
+        self.cosines = torch.from_numpy(co).to(device)
+        self.side_distances = torch.from_numpy(sd).to(device)
+        self.angle_increment = fov / (num_beams - 1)
+        self.c = nat.F110Beams(num_beams, fov, self.angle_increment,
+                               hostmaps.theta_index_increment(num_beams, fov, theta_dis),
+                               nat.ptr(self.scan_angles), nat.ptr(self.cosines), nat.ptr(self.side_distances))
+
+
+def empty_map_struct():
+    """A map struct with no DT bound: stepping with it raises ValueError like the reference
+    (laser_models.py:445-446 'Map is not set for scan simulator.')."""
+    return nat.F110Map()
+
+
+class Simulator(object):
+    """N x A batched simulator.  All state lives in persistent device buffers (SoA over the flat agent
+    index a = env*A + agent); the observation tensors returned by step() are VIEWS of those buffers
+    and are overwritten by the next step (the reference likewise returns aliases of internal arrays,
+    base_classes.py:594-602)."""
+
+    def __init__(self, params, num_agents, seed, time_step=0.01, ego_idx=0, integrator=Integrator.RK4,
+                 lidar_dist=0.0, num_envs=1, num_beams=1080, fov=4.7, device=None, noise_std=0.0,
+                 count_lookups=False):
+        nat.lib()   # fail loudly right away if the CUDA library is missing
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.num_agents = int(num_agents)
+        self.num_envs = int(num_envs)
+        self.seed = seed
+        self.time_step = time_step
+        self.ego_idx = ego_idx
+        self.params = params
+        self.integrator = integrator
+        self.lidar_dist = lidar_dist
+        self.num_beams, self.fov = num_beams, fov
+        if isinstance(integrator, Integrator):
+            integ = integrator.value
+        elif integrator in (1, 2):
+            integ = int(integrator)
+        else:
+            name = getattr(integrator, 'name', integrator)
+            raise SyntaxError("Invalid Integrator Specified. Provided %s. Please choose RK4 or Euler" % name)
+        N, A, B = self.num_envs, self.num_agents, num_beams
+        NA = N * A
+        dev = self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.params_dev = torch.from_numpy(np.tile(hostmaps.params_vector(params), (A, 1))).to(dev)
+        self.state = torch.zeros((7, NA), **f64)
+        self.steer_buf = torch.zeros((2, NA), **f64)
+        self.steer_cnt = torch.zeros((NA,), **i32)
+        self.scan_pose = torch.zeros((NA, 4), **f64)
+        self.agent_poses = torch.zeros((NA, 3), **f64)
+        self.scans = torch.zeros((NA, B), dtype=torch.float32, device=dev)
+        self.wall_flag = torch.zeros((NA,), **i32)
+        self.collisions = torch.zeros((NA,), **f64)
+        self.collision_idx = torch.full((NA,), -1, **i32)
+        # F110Env-level arrays (f110_env.py:165-189), batched
+        self.current_time = torch.zeros((N,), **f64)
+        self.lap_times = torch.zeros((NA,), **f64)
+        self.lap_counts = torch.zeros((NA,), **f64)
+        self.toggle_list = torch.zeros((NA,), **f64)
+        self.near_starts = torch.ones((NA,), **i32)
+        self.start_xs = torch.zeros((NA,), **f64)
+        self.start_ys = torch.zeros((NA,), **f64)
+        self.start_thetas = torch.zeros((NA,), **f64)
+        self.start_rot = torch.eye(2, **f64).reshape(1, 4).repeat(N, 1).contiguous()
+        self.done = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        self.checkpoint_done = torch.zeros((NA,), dtype=torch.uint8, device=dev)
+        self.lookup_counter = torch.zeros((1,), dtype=torch.int64, device=dev) if count_lookups else None
+        self.tick_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.beams = DeviceBeams(num_beams, fov, params, dev)
+        self.map = None
+        self._map_struct = empty_map_struct()
+        self._actions_dev = torch.zeros((NA, 2), **f64)
+        self.c = nat.F110Sim(
+            N, A, integ, ego_idx, time_step, lidar_dist, 0.005, float(params['length']), float(params['width']),
+            nat.ptr(self.params_dev), nat.ptr(self.state), nat.ptr(self.steer_buf), nat.ptr(self.steer_cnt),
+            nat.ptr(self.scan_pose), nat.ptr(self.agent_poses), nat.ptr(self.scans), nat.ptr(self.wall_flag),
+            nat.ptr(self.collisions), nat.ptr(self.collision_idx), nat.ptr(self.current_time),
+            nat.ptr(self.lap_times), nat.ptr(self.lap_counts), nat.ptr(self.toggle_list),
+            nat.ptr(self.near_starts), nat.ptr(self.start_xs), nat.ptr(self.start_ys),
+            nat.ptr(self.start_thetas), nat.ptr(self.start_rot), nat.ptr(self.done),
+            nat.ptr(self.checkpoint_done), nat.ptr(self.lookup_counter), nat.ptr(self.tick_counter),
+            float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        self._graph = None
+
+    # ------------------------------------------------------------------ configuration
+    def set_map(self, map_path, map_ext):
+        """base_classes.py:499-511 / laser_models.py:383-427 (load-time: PIL + yaml + scipy EDT on host)."""
+        self.set_device_map(DeviceMap.from_yaml(map_path, map_ext, self.device))
+
+    def set_device_map(self, device_map):
+        self.map = device_map
+        self._map_struct = device_map.c
+        self._graph = None
+
+    def update_params(self, params, agent_idx=-1):
+        """base_classes.py:514-534.  agent_idx < 0: every agent slot; else that slot in every env."""
+        pv = torch.from_numpy(hostmaps.params_vector(params)).to(self.device)
+        if agent_idx < 0:
+            self.params_dev[:] = pv
+        elif 0 <= agent_idx < self.num_agents:
+            self.params_dev[agent_idx] = pv
+        else:
+            raise IndexError('Index given is out of bounds for list of agents.')
+
+    def set_noise(self, std_dev, seed=None):
+        """Scan noise N(0, std_dev^2) (laser_models.py:429,450-452); 0 disables (parity runs)."""
+        self.c.noise_std = float(std_dev)
+        if seed is not None:
+            self.c.noise_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._graph = None
+
+    # ------------------------------------------------------------------ helpers
+    def _poses_tensor(self, poses):
+        N, A = self.num_envs, self.num_agents
+        p = torch.as_tensor(poses, dtype=torch.float64)
+        if p.dim() == 2:
+            if p.shape[0] != A:
+                raise ValueError('Number of poses for reset does not match number of agents.')
+            p = p.unsqueeze(0).expand(N, A, 3)
+        elif p.dim() != 3 or p.shape[0] != N or p.shape[1] != A:
+            raise ValueError('Number of poses for reset does not match number of agents.')
+        return p.to(self.device).contiguous()
+
+    def _actions_tensor(self, control_inputs):
+        N, A = self.num_envs, self.num_agents
+        a = control_inputs
+        if not (torch.is_tensor(a) and a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()
+                and a.numel() == N * A * 2):
+            a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, dtype=torch.float64)
+            if a.dim() == 2 and N > 1:
+                a = a.unsqueeze(0).expand(N, A, 2)
+            if a.numel() != N * A * 2:
+                raise ValueError('control_inputs must have shape (num_envs, num_agents, 2)')
+            self._actions_dev.copy_(a.reshape(N * A, 2), non_blocking=True)
+            a = self._actions_dev
+        return a
+
+    def _mask_ptr(self, env_mask):
+        if env_mask is None:
+            return None, None
+        m = torch.as_tensor(env_mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        if m.numel() != self.num_envs:
+            raise ValueError('env_mask must have num_envs entries')
+        return m, nat.ptr(m)
+
+    # ------------------------------------------------------------------ reference-surface methods
+    def reset(self, poses, env_mask=None):
+        """Simulator.reset (base_classes.py:614-630): zero state, place agents, empty steer FIFO.
+        poses: (A,3) broadcast to every env, or (N,A,3).  env_mask (N,) bool: partial reset."""
+        p = self._poses_tensor(poses)
+        m, mp = self._mask_ptr(env_mask)
+        nat.check(nat.lib().f110_reset(C.byref(self.c), nat.ptr(p), mp, _stream_ptr(self.device)))
+
+    def env_reset(self, poses, env_mask=None):
+        """Counters and start frame of F110Env.reset (f110_env.py:319-331) + Simulator.reset."""
+        p = self._poses_tensor(poses)
+        m, mp = self._mask_ptr(env_mask)
+        L = nat.lib()
+        nat.check(L.f110_env_reset(C.byref(self.c), nat.ptr(p), mp, _stream_ptr(self.device)))
+        nat.check(L.f110_reset(C.byref(self.c), nat.ptr(p), mp, _stream_ptr(self.device)))
+
+    def step(self, control_inputs):
+        """Simulator.step (base_classes.py:553-612). control_inputs (N,A,2) = (steer, speed)."""
+        a = self._actions_tensor(control_inputs)
+        nat.check(nat.lib().f110_step(C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c),
+                                      nat.ptr(a), _stream_ptr(self.device)))
+        return self.observations()
+
+    def env_post_step(self):
+        """Tail of F110Env.step: time + lap logic + done (f110_env.py:294-302, 204-246)."""
+        nat.check(nat.lib().f110_env_post_step(C.byref(self.c), _stream_ptr(self.device)))
+
+    def autoreset(self, start_poses, pose_gap=23, seed=12345):
+        """Reset every env whose ego collided to a hashed draw from start_poses (device (K,3) fp64)."""
+        nat.check(nat.lib().f110_autoreset(C.byref(self.c), nat.ptr(start_poses), start_poses.shape[0],
+                                           pose_gap, int(seed), 0, _stream_ptr(self.device)))
+
+    def observations(self):
+        N, A, B = self.num_envs, self.num_agents, self.num_beams
+        st = self.state
+        return {'ego_idx': self.ego_idx,
+                'scans': self.scans.view(N, A, B),
+                'poses_x': st[0].view(N, A), 'poses_y': st[1].view(N, A), 'poses_theta': st[4].view(N, A),
+                'linear_vels_x': st[3].view(N, A),
+                'linear_vels_y': torch.zeros((N, A), dtype=torch.float64, device=self.device),
+                'ang_vels_z': st[5].view(N, A),
+                'collisions': self.collisions.view(N, A)}
+
+    # ------------------------------------------------------------------ throughput paths
+    def capture_graph(self, actions, autoreset_poses=None, pose_gap=23, autoreset_seed=12345, env_level=False):
+        """Capture one tick (f110_step [+ env_post_step] [+ autoreset]) reading `actions` (a persistent
+        device tensor the caller overwrites between replays) into a CUDA graph."""
+        assert actions.is_cuda and actions.dtype == torch.float64 and actions.is_contiguous()
+        L = nat.lib()
+
+        def tick():
+            nat.check(L.f110_step(C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c),
+                                  nat.ptr(actions), _stream_ptr(self.device)))
+            if env_level:
+                nat.check(L.f110_env_post_step(C.byref(self.c), _stream_ptr(self.device)))
+            if autoreset_poses is not None:
+                nat.check(L.f110_autoreset(C.byref(self.c), nat.ptr(autoreset_poses), autoreset_poses.shape[0],
+                                           pose_gap, int(autoreset_seed), 0, _stream_ptr(self.device)))
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            tick()      # warm-up outside capture (module load, first-launch work)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            tick()
+        self._graph = g
+        self._graph_keep = (actions, autoreset_poses)
+        return g
+
+    def replay(self):
+        self._graph.replay()
+
+    def make_host_io(self, with_scans=True):
+        """Pinned host buffers for step_host()."""
+        N, A, B = self.num_envs, self.num_agents, self.num_beams
+        NA = N * A
+        io = {'actions': torch.zeros((NA, 2), dtype=torch.float64).pin_memory(),
+              'scans': torch.zeros((NA, B), dtype=torch.float32).pin_memory() if with_scans else None,
+              'state': torch.zeros((7, NA), dtype=torch.float64).pin_memory(),
+              'collisions': torch.zeros((NA,), dtype=torch.float64).pin_memory(),
+              'done': torch.zeros((N,), dtype=torch.uint8).pin_memory(),
+              'lap_times': torch.zeros((NA,), dtype=torch.float64).pin_memory(),
+              'lap_counts': torch.zeros((NA,), dtype=torch.float64).pin_memory()}
+        io['_struct'] = nat.F110HostObs(nat.ptr(io['scans']), nat.ptr(io['state']), nat.ptr(io['collisions']),
+                                        nat.ptr(io['done']), nat.ptr(io['lap_times']), nat.ptr(io['lap_counts']))
+        return io
+
+    def step_host(self, io):
+        """One tick through HOST buffers (C ABI f110_step_host): H2D actions, step, env_post_step,
+        D2H observation, stream sync.  io from make_host_io(); fill io['actions'] first."""
+        nat.check(nat.lib().f110_step_host(C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c),
+                                           nat.ptr(io['actions']), nat.ptr(self._actions_dev),
+                                           C.byref(io['_struct']), _stream_ptr(self.device)))
+        return io
+
+    def step_profile(self, control_inputs):
+        """One tick with CUDA events around each kernel -> (dynamics_ms, raymarch_ms, finalize_ms)."""
+        a = self._actions_tensor(control_inputs)
+        ms = (C.c_float * 3)()
+        nat.check(nat.lib().f110_step_profile(C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c),
+                                              nat.ptr(a), ms, _stream_ptr(self.device)))
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def lookups(self):
+        return int(self.lookup_counter.item()) if self.lookup_counter is not None else None

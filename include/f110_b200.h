@@ -1,0 +1,176 @@
+/*
+ * f110_b200.h — C ABI of the B200-native batched F1TENTH hot path (libf110_b200.so).
+ *
+ * The reference (f1tenth/f1tenth_gym) is pure Python + numba and has no FFI of its own; its
+ * boundary for this path is the Python surface  F110Env -> Simulator -> @njit kernels.  Each entry
+ * point below replaces one of those Python-level interfaces (cited file:line, paths relative to
+ * gym/f110_gym/envs/ of the reference).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to bind them.
+ *
+ * Conventions
+ *   - plain C types only; every pointer inside the structs is a DEVICE pointer owned by the caller
+ *     (the Python host side allocates them as torch CUDA tensors), except in the *_host entry points.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns 0 on success or a negative f110_status; nothing is printed or thrown.
+ *   - all arithmetic is IEEE fp64 without FMA contraction (the reference's numba path emits none);
+ *     scans are written as fp32 (= fp32(reference fp64 value), <= 1.9e-6 m at 30 m).
+ *   - agents are indexed a = env * num_agents + agent ("flat agent index"), SoA over a.
+ */
+#ifndef F110_B200_H
+#define F110_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F110_ABI_VERSION 1
+#define F110_NPARAM 18     /* mu C_Sf C_Sr lf lr h m I s_min s_max sv_min sv_max v_switch a_max v_min v_max width length
+                              (key order of the default dict, f110_env.py:130) */
+#define F110_NSTATE 7      /* x y steer v yaw yaw_rate slip   (base_classes.py:97) */
+
+typedef enum {
+    F110_OK = 0,
+    F110_ERR_INVALID = -1,      /* bad argument (NULL pointer, non-positive size, ...)            */
+    F110_ERR_NO_MAP = -2,       /* scan before a map is set (laser_models.py:445-446 ValueError)  */
+    F110_ERR_CUDA = -3,         /* a CUDA runtime call failed; see f110_last_cuda_error()          */
+    F110_ERR_INTEGRATOR = -4,   /* integrator not RK4(1)/Euler(2) (base_classes.py:397-398)       */
+    F110_ERR_POSE_COUNT = -5,   /* reset pose count mismatch (base_classes.py:625-626 ValueError) */
+    F110_ERR_AGENT_INDEX = -6   /* update_params index out of range (base_classes.py:534)         */
+} f110_status;
+
+/* ScanSimulator2D state after set_map (laser_models.py:348-427). */
+typedef struct {
+    int32_t height, width;
+    double resolution, orig_x, orig_y, orig_c, orig_s;
+    double eps, max_range;          /* 1e-4, 30.0 (laser_models.py:360) */
+    int32_t theta_dis;              /* 2000 */
+    int32_t fast_path;              /* 1 iff resolution is a power of two and orig_c==1, orig_s==0:
+                                       x/res == x*(1/res) exactly and the rotation is the identity */
+    double dt_oob;                  /* dt[-1,-1]: what an off-map ray reads (laser_models.py:79-81) */
+    const double *dt;               /* [height*width] fp64 distance transform, row 0 = image bottom */
+    const double *sines, *cosines;  /* [theta_dis]  sin/cos(linspace(0, 2pi, theta_dis)) (:379-381) */
+} f110_map;
+
+/* Beam tables RaceCar.__init__ builds once (base_classes.py:122-158) + ScanSimulator2D.__init__ (:360-368). */
+typedef struct {
+    int32_t num_beams;
+    double fov, angle_increment, theta_index_increment;
+    const double *scan_angles, *cosines, *side_distances;   /* [num_beams] */
+} f110_beams;
+
+/* Simulator / RaceCar / F110Env state for N envs x A agents, SoA, caller-owned device memory. */
+typedef struct {
+    int32_t num_envs, num_agents;
+    int32_t integrator;             /* 1 = RK4, 2 = Euler (base_classes.py:40-42) */
+    int32_t ego_idx;
+    double timestep, lidar_dist, ttc_thresh;   /* 0.01, 0.0, 0.005 (base_classes.py:115) */
+    double sim_length, sim_width;   /* Simulator.params['length'/'width'] used by check_collision (:549) */
+    const double *params;           /* [A][F110_NPARAM] per agent slot (update_params, base_classes.py:514-534) */
+    double *state;                  /* [F110_NSTATE][N*A] */
+    double *steer_buf;              /* [2][N*A]   steering delay FIFO, row 0 = newest (base_classes.py:270-278) */
+    int32_t *steer_cnt;             /* [N*A] */
+    double *scan_pose;              /* [N*A][4]   (scan_x, scan_y, yaw, theta_index0) written by the dynamics kernel */
+    double *agent_poses;            /* [N*A][3]   Simulator.agent_poses snapshot (base_classes.py:574) */
+    float *scans;                   /* [N*A][num_beams] */
+    int32_t *wall_flag;             /* [N*A]      RaceCar.in_collision (iTTC) */
+    double *collisions;             /* [N*A]      obs['collisions'] (0./1.) */
+    int32_t *collision_idx;         /* [N*A]      Simulator.collision_idx (-1 = none) */
+    /* F110Env level (f110_env.py:165-189); may be NULL if f110_env_post_step is never called */
+    double *current_time;           /* [N] */
+    double *lap_times, *lap_counts, *toggle_list;   /* [N*A] */
+    int32_t *near_starts;           /* [N*A] */
+    double *start_xs, *start_ys, *start_thetas;     /* [N*A] */
+    double *start_rot;              /* [N][4] */
+    uint8_t *done;                  /* [N] */
+    uint8_t *checkpoint_done;       /* [N*A]  info['checkpoint_done'] */
+    unsigned long long *lookup_counter;   /* optional [1]: total DT lookups (roofline denominator); NULL = off */
+    unsigned long long *tick_counter;     /* optional [1]: incremented by every f110_step; keys the noise stream
+                                             and the auto-reset draw so that CUDA-graph replays stay distinct */
+    /* scan noise (laser_models.py:429,450-452): N(0, noise_std^2) per beam, added before iTTC; 0 = off */
+    double noise_std;
+    uint64_t noise_seed;
+} f110_sim;
+
+int f110_abi_version(void);
+const char *f110_status_string(int status);
+const char *f110_last_cuda_error(void);
+
+/* ---- the per-tick hot path -------------------------------------------------------------------- */
+
+/* Simulator.step (base_classes.py:553-612): pid + RK4/Euler dynamics -> 1080-beam ray-march (+fused
+ * iTTC) -> GJK, wall-hit state zeroing, opponent ray-cast.  actions: device [N*A][2] = (steer, speed).
+ * Launches 3 kernels on `stream`; no host synchronisation. */
+int f110_step(const f110_sim *sim, const f110_map *map, const f110_beams *beams,
+              const double *actions, void *stream);
+
+/* f110_step with CUDA events recorded on `stream` around each of its three kernels; synchronises and
+ * returns their durations in milliseconds: kernel_ms[0..2] = dynamics, ray-march, finalize (host array).
+ * Measurement aid for bench.py's roofline figure; not for the hot loop. */
+int f110_step_profile(const f110_sim *sim, const f110_map *map, const f110_beams *beams,
+                      const double *actions, float *kernel_ms, void *stream);
+
+/* Simulator.reset / RaceCar.reset (base_classes.py:183-204, 614-630) for the envs whose env_mask
+ * byte is non-zero (env_mask == NULL: all).  poses: device [N*A][3].  No tick is executed. */
+int f110_reset(const f110_sim *sim, const double *poses, const uint8_t *env_mask, void *stream);
+
+/* The counters/start-frame part of F110Env.reset (f110_env.py:319-331) for masked envs. */
+int f110_env_reset(const f110_sim *sim, const double *poses, const uint8_t *env_mask, void *stream);
+
+/* F110Env.step tail: time, _check_done lap logic (f110_env.py:204-246, 294-302) -> done, lap arrays. */
+int f110_env_post_step(const f110_sim *sim, void *stream);
+
+/* Benchmark/RL convenience (no reference equivalent; SURVEY.md 8d policy): every env whose ego has
+ * collisions != 0 is reset (Simulator.reset + env counters) to start_poses[k], k drawn from a
+ * counter-based hash of (seed, tick, env); agent i takes start_poses[(k - pose_gap*i) mod K]. */
+int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_start, int32_t pose_gap,
+                   uint64_t seed, uint64_t tick, void *stream);
+
+/* Same tick through HOST buffers: copies actions H2D, runs f110_step (+ f110_env_post_step when the
+ * lap arrays are bound), copies the observation D2H and synchronises the stream.
+ * Any output pointer may be NULL to skip that copy.  Host buffers should be pinned. */
+typedef struct {
+    float *scans;           /* [N*A][B] */
+    double *state;          /* [7][N*A] */
+    double *collisions;     /* [N*A] */
+    uint8_t *done;          /* [N] */
+    double *lap_times, *lap_counts;   /* [N*A] */
+} f110_host_obs;
+int f110_step_host(const f110_sim *sim, const f110_map *map, const f110_beams *beams,
+                   const double *actions_host, double *actions_dev_scratch, const f110_host_obs *out,
+                   void *stream);
+
+/* ---- standalone kernels (unit-parity surface; device pointers) ------------------------------- */
+
+/* ScanSimulator2D.scan without noise / get_scan (laser_models.py:148-186, 429-454): M poses -> [M][B]. */
+int f110_scan(const f110_map *map, const f110_beams *beams, const double *poses /* [M][3] */, int32_t M,
+              float *out_f32 /* [M][B] or NULL */, double *out_f64 /* [M][B] or NULL */,
+              unsigned long long *lookup_counter /* [1] or NULL */, void *stream);
+/* vehicle_dynamics_st (dynamic_models.py:123-176): x [M][7], u [M][2], params [18] -> f [M][7]. */
+int f110_vehicle_dynamics_st(const double *x, const double *u, const double *params, int32_t M, double *f,
+                             void *stream);
+/* pid (dynamic_models.py:178-221): in [M][4] = (speed, steer, current_speed, current_steer) -> out [M][2] = (accl, sv). */
+int f110_pid(const double *in, const double *params, int32_t M, double *out, void *stream);
+/* get_vertices (collision_models.py:237-260): poses [M][3] -> [M][4][2] (rl, rr, fr, fl). */
+int f110_get_vertices(const double *poses, double length, double width, int32_t M, double *out, void *stream);
+/* collision (GJK, collision_models.py:113-182): va, vb [M][4][2] -> out [M] 0/1. */
+int f110_collision(const double *va, const double *vb, int32_t M, int32_t *out, void *stream);
+/* collision_multiple (collision_models.py:184-212): verts [M][n][4][2] -> collisions [M][n], collision_idx [M][n]. */
+int f110_collision_multiple(const double *verts, int32_t M, int32_t n, double *collisions, double *collision_idx,
+                            void *stream);
+/* check_ttc_jit (laser_models.py:188-217): scans [M][B] fp64, vel [M] -> out [M] 0/1. */
+int f110_check_ttc(const f110_beams *beams, const double *scans, const double *vel, double ttc_thresh, int32_t M,
+                   int32_t *out, void *stream);
+/* ray_cast (laser_models.py:318-346): pose [M][3], opponent vertices [M][4][2], scans [M][B] fp32 modified in
+ * place; window [M][2] (min_ind, max_ind of get_blocked_view_indices :282-315) optional. */
+int f110_ray_cast(const f110_beams *beams, const double *poses, const double *opp_vertices, int32_t M,
+                  float *scans, int32_t *window, void *stream);
+/* Seeded scan noise (laser_models.py:450-452; N(0, std^2) per beam).  Counter-based Philox-4x32 +
+ * Box-Muller; statistical, not bit, parity with numpy's PCG64 stream. */
+int f110_scan_noise(float *scans, int64_t count, double std_dev, uint64_t seed, uint64_t offset, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F110_B200_H */

@@ -69,7 +69,7 @@ def ncu_traffic(workload):
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.005):
         threading.Thread.__init__(self, daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None

@@ -24,7 +24,7 @@ class F110Map(C.Structure):
                 ('eps', C.c_double), ('max_range', C.c_double),
                 ('theta_dis', C.c_int32), ('fast_path', C.c_int32),
                 ('dt_oob', C.c_double),
-                ('dt', _dp), ('sines', _dp), ('cosines', _dp)]
+                ('dt', _dp), ('dt_cells', _dp), ('sines', _dp), ('cosines', _dp)]
 
 
 class F110Beams(C.Structure):

@@ -38,7 +38,7 @@ static int cuda_fail(cudaError_t e, const char *where) {
 
 static MapView make_view(const f110_map *m) {
     MapView v;
-    v.dt = m->dt; v.sines = m->sines; v.cosines = m->cosines;
+    v.dt = m->dt; v.dt_cells = m->dt_cells; v.sines = m->sines; v.cosines = m->cosines;
     v.orig_x = m->orig_x; v.orig_y = m->orig_y; v.orig_c = m->orig_c; v.orig_s = m->orig_s;
     v.resolution = m->resolution; v.inv_resolution = 1.0 / m->resolution;
     v.x_max = m->width * m->resolution;    // `width * resolution` (laser_models.py:79)
@@ -155,6 +155,68 @@ __global__ void __launch_bounds__(256) k_raymarch(MapView m, BeamView bv, MarchA
         if (g.out_f64) g.out_f64[gid] = range;
     }
     if (g.lookup_counter) {
+        unsigned n = (unsigned)nlook;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(g.lookup_counter, (unsigned long long)n);
+    }
+}
+
+// ------------------------------------------------------------------------------------ k_raymarch_cells
+// Fast path (power-of-two resolution, unrotated origin): RM_T-thread blocks, each block owns RM_T
+// consecutive beams of ONE agent (17 blocks of 64 cover 1080 beams with 0.7 % padding), so the pose is
+// block-uniform, the lanes of a warp walk neighbouring DT cells, and the block scheduler balances load
+// at a 64-beam granularity.  See lidar.cuh for the cell-unit march.
+#define RM_T 64
+template <bool STANDALONE, bool COUNT>
+__global__ void __launch_bounds__(RM_T) k_raymarch_cells(MapView m, BeamView bv, MarchArgs g, int blocks_per_agent) {
+    const unsigned a = blockIdx.x / (unsigned)blocks_per_agent;
+    const int i = (int)(blockIdx.x - a * (unsigned)blocks_per_agent) * RM_T + (int)threadIdx.x;
+    const int B = bv.num_beams;
+    int nlook = 0;
+    if (i < B) {
+        double px, py, ti0;
+        if (STANDALONE) {
+            px = g.scan_pose[3 * (size_t)a];
+            py = g.scan_pose[3 * (size_t)a + 1];
+            ti0 = theta_index0(g.scan_pose[3 * (size_t)a + 2], bv.fov, m.theta_dis_f);
+        } else {
+            const double2 *sp = reinterpret_cast<const double2 *>(g.scan_pose) + 2 * (size_t)a;
+            const double2 xy = __ldg(sp), yt = __ldg(sp + 1);
+            px = xy.x; py = xy.y; ti0 = yt.y;
+        }
+        const int ti = beam_theta_index(ti0, i, bv.theta_index_increment, m.theta_dis_f);
+        const double s = __ldg(m.sines + ti), c = __ldg(m.cosines + ti);
+        double range;
+        if (fabs(px) < 1e8 && fabs(py) < 1e8) {
+            CellConsts k;
+            k.ox = m.orig_x * m.inv_resolution; k.oy = m.orig_y * m.inv_resolution;
+            k.eps = m.eps * m.inv_resolution; k.tmax = m.max_range * m.inv_resolution;
+            k.width = (unsigned)m.width; k.height = (unsigned)m.height;
+            k.last = (unsigned)m.width * (unsigned)m.height - 1u;
+            // pin the loop constants in registers (otherwise they are re-fetched from the constant bank
+            // with LDCU inside the march loop, costing issue slots)
+            asm volatile("" : "+d"(k.ox), "+d"(k.oy), "+d"(k.eps), "+d"(k.tmax));
+            asm volatile("" : "+r"(k.width), "+r"(k.height), "+r"(k.last));
+            const double T = trace_ray_cells<COUNT>(m.dt_cells, px * m.inv_resolution, py * m.inv_resolution, s, c, k, nlook);
+            range = ((T > k.tmax) ? k.tmax : T) * m.resolution;
+        } else {
+            range = trace_ray<false>(m, px, py, s, c, nlook);   // absurd coordinates: literal reference arithmetic
+        }
+        if (g.noise_std > 0.0) {
+            unsigned long long tick = g.tick_counter ? *g.tick_counter : 0ull;
+            range = range + g.noise_std * normal_sample(g.noise_seed, tick, (uint64_t)a * (uint64_t)B + (uint64_t)i);
+        }
+        if (g.wall_flag) {
+            const double v = __ldg(g.vel + a);
+            if (ttc_hit(range, v, __ldg(bv.cosines + i), __ldg(bv.side_distances + i), g.ttc_thresh))
+                atomicOr(g.wall_flag + a, 1);
+        }
+        const size_t o = (size_t)a * (size_t)B + (size_t)i;
+        if (g.out_f32) g.out_f32[o] = (float)range;
+        if (g.out_f64) g.out_f64[o] = range;
+    }
+    if (COUNT) {
         unsigned n = (unsigned)nlook;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
@@ -471,16 +533,26 @@ static int check_beams(const f110_beams *b) {
 
 static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArgs &g, bool fast, bool standalone,
                            cudaStream_t st) {
+    if (fast && mv.dt_cells && (unsigned long long)mv.width * (unsigned long long)mv.height < (1ull << 32)) {
+        const int bpa = (bv.num_beams + RM_T - 1) / RM_T;
+        const long long blocks = (g.total / bv.num_beams) * bpa;
+        if (blocks <= 0 || blocks > 0x7fffffffll) return F110_ERR_INVALID;
+        const bool count = g.lookup_counter != nullptr;
+        if (standalone) {
+            if (count) k_raymarch_cells<true, true><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+            else k_raymarch_cells<true, false><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+        } else {
+            if (count) k_raymarch_cells<false, true><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+            else k_raymarch_cells<false, false><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+        }
+        LAUNCH_CHECK("k_raymarch_cells");
+        return F110_OK;
+    }
     const int threads = 256;
     const long long blocks = (g.total + threads - 1) / threads;
     if (blocks <= 0 || blocks > 0x7fffffffll) return F110_ERR_INVALID;
-    if (standalone) {
-        if (fast) k_raymarch<true, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
-        else k_raymarch<false, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
-    } else {
-        if (fast) k_raymarch<true, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
-        else k_raymarch<false, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
-    }
+    if (standalone) k_raymarch<false, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+    else k_raymarch<false, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
     LAUNCH_CHECK("k_raymarch");
     return F110_OK;
 }

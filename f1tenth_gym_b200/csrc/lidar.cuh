@@ -12,12 +12,52 @@ namespace f110 {
 
 struct MapView {
     const double *__restrict__ dt;
+    const double *__restrict__ dt_cells;   // dt / resolution (cell units); fast path only, else NULL
     const double *__restrict__ sines;
     const double *__restrict__ cosines;
     double orig_x, orig_y, orig_c, orig_s, resolution, inv_resolution, x_max, y_max;
     double eps, max_range, dt_oob, theta_dis_f;
     int32_t height, width, theta_dis;
 };
+
+// ---- fast path in CELL UNITS --------------------------------------------------------------------
+// When resolution = 2^-k and the map origin is unrotated, scaling every length by 1/res is exact in
+// fp64 and commutes with rounding: X = x/res, D = d/res satisfy fl(X + fl(D*c)) = fl(x + fl(d*c))/res.
+// Marching in cell units removes the two multiplies by 1/res per lookup; floor() is taken with one
+// round-down add of 2^52+2^51 on the fp64 pipe (F2I.F64 would go through the quarter-rate XU pipe),
+// the four fp64 bounds tests become two unsigned compares, and an off-map lookup is redirected to the
+// last cell, which holds exactly the value the reference reads through dt[-1,-1].
+struct CellConsts {
+    double ox, oy;        // orig / res
+    double eps, tmax;     // eps / res, max_range / res
+    unsigned width, height, last;
+};
+
+__device__ __forceinline__ unsigned cell_index(double X, double Y, const CellConsts &k) {
+    const double MAGIC = 6755399441055744.0;   // 2^52 + 2^51
+    int c = __double2loint(__dadd_rd(X - k.ox, MAGIC));
+    int r = __double2loint(__dadd_rd(Y - k.oy, MAGIC));
+    bool inb = ((unsigned)c < k.width) && ((unsigned)r < k.height);
+    return inb ? (unsigned)r * k.width + (unsigned)c : k.last;
+}
+
+// trace_ray (laser_models.py:106-146) in cell units; returns total (cell units, unclamped > tmax possible)
+template <bool COUNT>
+__device__ __forceinline__ double trace_ray_cells(const double *__restrict__ dtc, double X, double Y, double s,
+                                                  double c, const CellConsts &k, int &nlook) {
+    double D = __ldg(dtc + cell_index(X, Y, k));
+    double T = D;
+    int n = 1;
+    while (D > k.eps && T <= k.tmax) {
+        X = X + D * c;
+        Y = Y + D * s;
+        D = __ldg(dtc + cell_index(X, Y, k));
+        T = T + D;
+        if (COUNT) n++;
+    }
+    nlook = n;
+    return T;
+}
 
 // laser_models.py:55-104 xy_2_rc + distance_transform.
 // FAST: resolution is a power of two and the origin is unrotated, so x_rot == x - orig_x exactly,
@@ -76,10 +116,10 @@ __device__ __forceinline__ double theta_index0(double yaw, double fov, double th
 // (2e-6-probability) case the exact sequential recurrence is replayed for this beam.
 __device__ __forceinline__ int beam_theta_index(double ti0, int i, double inc, double theta_dis_f) {
     double v = ti0 + (double)i * inc;
-    v = v - theta_dis_f * floor(v / theta_dis_f);
-    double fl = floor(v);
-    double fr = v - fl;
-    if (fr < 1e-6 || fr > 1.0 - 1e-6 || v >= theta_dis_f) {
+    while (v >= theta_dis_f) v -= theta_dis_f;
+    int iv = (int)v;
+    double fr = v - (double)iv;
+    if (fr < 1e-6 || fr > 1.0 - 1e-6) {
         double t = ti0;
         for (int k = 0; k < i; k++) {
             t += inc;
@@ -87,14 +127,18 @@ __device__ __forceinline__ int beam_theta_index(double ti0, int i, double inc, d
         }
         return (int)t;
     }
-    return (int)fl;
+    return iv;
 }
 
 // laser_models.py:188-217 check_ttc_jit, one beam (error_model='numpy': x/0 -> inf/nan, compares false)
 __device__ __forceinline__ bool ttc_hit(double range, double vel, double cos_i, double side_i, double thresh) {
     if (vel == 0.0) return false;
     double proj_vel = vel * cos_i;
-    double ttc = (range - side_i) / proj_vel;
+    double a = range - side_i;
+    // necessary condition for 0 <= fl(a/p) < thresh, with margin; the exact IEEE division (a ~30-instruction
+    // sequence) then only runs for beams that are actually near a collision
+    if (!(fabs(a) <= thresh * fabs(proj_vel) * 1.000001)) return false;
+    double ttc = a / proj_vel;
     return (ttc < thresh) && (ttc >= 0.0);
 }
 

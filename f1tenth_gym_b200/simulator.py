@@ -42,12 +42,14 @@ class DeviceMap(object):
         self.theta_dis = theta_dis
         sines, cosines = hostmaps.angle_lut(theta_dis)
         self.dt = torch.from_numpy(host_map.dt).to(device)
+        # cell-unit copy for the fast path (res = 2^-k: the division is an exact exponent shift)
+        self.dt_cells = torch.from_numpy(host_map.dt / host_map.resolution).to(device) if host_map.fast_path else None
         self.sines = torch.from_numpy(sines).to(device)
         self.cosines = torch.from_numpy(cosines).to(device)
         self.c = nat.F110Map(host_map.height, host_map.width, host_map.resolution, host_map.orig_x,
                              host_map.orig_y, host_map.orig_c, host_map.orig_s, eps, max_range, theta_dis,
-                             host_map.fast_path, host_map.dt_oob, nat.ptr(self.dt), nat.ptr(self.sines),
-                             nat.ptr(self.cosines))
+                             host_map.fast_path, host_map.dt_oob, nat.ptr(self.dt), nat.ptr(self.dt_cells),
+                             nat.ptr(self.sines), nat.ptr(self.cosines))
 
     @classmethod
     def from_yaml(cls, map_path, map_ext, device, **kw):

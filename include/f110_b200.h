@@ -50,6 +50,8 @@ typedef struct {
                                        x/res == x*(1/res) exactly and the rotation is the identity */
     double dt_oob;                  /* dt[-1,-1]: what an off-map ray reads (laser_models.py:79-81) */
     const double *dt;               /* [height*width] fp64 distance transform, row 0 = image bottom */
+    const double *dt_cells;         /* [height*width] dt / resolution (exact when fast_path), or NULL: enables
+                                       the cell-unit march; ignored unless fast_path */
     const double *sines, *cosines;  /* [theta_dis]  sin/cos(linspace(0, 2pi, theta_dis)) (:379-381) */
 } f110_map;
 

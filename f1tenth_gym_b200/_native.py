@@ -24,13 +24,14 @@ class F110Map(C.Structure):
                 ('eps', C.c_double), ('max_range', C.c_double),
                 ('theta_dis', C.c_int32), ('fast_path', C.c_int32),
                 ('dt_oob', C.c_double),
-                ('dt', _dp), ('dt_cells', _dp), ('sines', _dp), ('cosines', _dp)]
+                ('dt', _dp), ('dt_cells', _dp), ('dt_codes', _dp), ('dt_lut', _dp),
+                ('sines', _dp), ('cosines', _dp), ('sincos', _dp)]
 
 
 class F110Beams(C.Structure):
     _fields_ = [('num_beams', C.c_int32),
                 ('fov', C.c_double), ('angle_increment', C.c_double), ('theta_index_increment', C.c_double),
-                ('scan_angles', _dp), ('cosines', _dp), ('side_distances', _dp)]
+                ('scan_angles', _dp), ('cosines', _dp), ('side_distances', _dp), ('cos_side', _dp)]
 
 
 class F110Sim(C.Structure):
@@ -45,6 +46,7 @@ class F110Sim(C.Structure):
                 ('near_starts', _dp), ('start_xs', _dp), ('start_ys', _dp), ('start_thetas', _dp),
                 ('start_rot', _dp), ('done', _dp), ('checkpoint_done', _dp),
                 ('lookup_counter', _dp), ('tick_counter', _dp),
+                ('march_cost', _dp), ('march_order', _dp), ('march_count', _dp), ('march_ipa', C.c_int32),
                 ('noise_std', C.c_double), ('noise_seed', C.c_uint64)]
 
 

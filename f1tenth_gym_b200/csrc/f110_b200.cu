@@ -11,11 +11,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/f110_b200.h"
 #include "collision.cuh"
 #include "dynamics.cuh"
 #include "lidar.cuh"
+#include "march.cuh"
 
 namespace f110 {
 
@@ -38,7 +40,8 @@ static int cuda_fail(cudaError_t e, const char *where) {
 
 static MapView make_view(const f110_map *m) {
     MapView v;
-    v.dt = m->dt; v.dt_cells = m->dt_cells; v.sines = m->sines; v.cosines = m->cosines;
+    v.dt = m->dt; v.dt_cells = m->dt_cells; v.dt_codes = m->dt_codes; v.dt_lut = m->dt_lut;
+    v.sines = m->sines; v.cosines = m->cosines;
     v.orig_x = m->orig_x; v.orig_y = m->orig_y; v.orig_c = m->orig_c; v.orig_s = m->orig_s;
     v.resolution = m->resolution; v.inv_resolution = 1.0 / m->resolution;
     v.x_max = m->width * m->resolution;    // `width * resolution` (laser_models.py:79)
@@ -64,10 +67,50 @@ static BeamView make_view(const f110_beams *b) {
     return v;
 }
 
+// Work queue of the persistent march kernel (march.cuh): sort the 32-beam items into [very heavy | heavy |
+// light] by the maximum lookup count they recorded in the previous tick.  One thread per item; runs as the
+// extra blocks of k_dynamics (it only reads march_cost, which the reset kernels mark as unknown).
+__device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned w, unsigned items) {
+    const unsigned lane = threadIdx.x & 31u;
+    int cls = -1;
+    unsigned packed = 0;
+    if (w < items) {
+        const unsigned ipa = (unsigned)s.march_ipa;
+        const unsigned a = w / ipa, j = w - a * ipa;
+        const unsigned c = s.march_cost[w];
+        unsigned m = c;
+        if (c != F110_Q_UNKNOWN) {
+            if (j > 0) { const unsigned cl = s.march_cost[w - 1]; if (cl != F110_Q_UNKNOWN) m = max(m, cl); }
+            if (j + 1 < ipa) { const unsigned cr = s.march_cost[w + 1]; if (cr != F110_Q_UNKNOWN) m = max(m, cr); }
+        }
+        cls = (c == F110_Q_UNKNOWN || c >= F110_Q_VERY_HEAVY) ? 0 : (m >= F110_Q_HEAVY) ? 1 : 2;
+        packed = (a << 8) | j;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const unsigned msk = __ballot_sync(0xffffffffu, cls == k);
+        if (msk) {
+            unsigned base = 0;
+            const int leader = __ffs(msk) - 1;
+            if ((int)lane == leader) base = atomicAdd(s.march_count + k, (unsigned)__popc(msk));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cls == k) {
+                const unsigned slot = base + (unsigned)__popc(msk & ((1u << lane) - 1u));
+                if (slot < items) s.march_order[(size_t)k * items + slot] = packed;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ k_dynamics
 __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
-                                                  double theta_dis_f) {
+                                                  double theta_dis_f, int dyn_blocks) {
     const int NA = s.num_envs * s.num_agents;
+    if ((int)blockIdx.x >= dyn_blocks) {     // extra blocks: build the march work queue (block-uniform branch)
+        build_march_order(s, (blockIdx.x - (unsigned)dyn_blocks) * blockDim.x + threadIdx.x,
+                          (unsigned)NA * (unsigned)s.march_ipa);
+        return;
+    }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= NA) return;
     const double *p = s.params + (size_t)(a % s.num_agents) * F110_NPARAM;
@@ -168,13 +211,16 @@ __global__ void __launch_bounds__(256) k_raymarch(MapView m, BeamView bv, MarchA
 // block-uniform, the lanes of a warp walk neighbouring DT cells, and the block scheduler balances load
 // at a 64-beam granularity.  See lidar.cuh for the cell-unit march.
 #define RM_T 64
-template <bool STANDALONE, bool COUNT>
-__global__ void __launch_bounds__(RM_T) k_raymarch_cells(MapView m, BeamView bv, MarchArgs g, int blocks_per_agent) {
+// NB beams per thread (adjacent beams i, i+1: strongly correlated step counts) give NB independent
+// dependent-load chains per lane: the march is latency-bound (long-scoreboard stalls dominate), so
+// memory-level parallelism per warp matters more than instruction count.
+template <bool STANDALONE, bool COUNT, int NB, int MINB, bool CODED>
+__global__ void __launch_bounds__(RM_T, MINB) k_raymarch_cells(MapView m, BeamView bv, MarchArgs g, int blocks_per_agent) {
     const unsigned a = blockIdx.x / (unsigned)blocks_per_agent;
-    const int i = (int)(blockIdx.x - a * (unsigned)blocks_per_agent) * RM_T + (int)threadIdx.x;
+    const int i0 = ((int)(blockIdx.x - a * (unsigned)blocks_per_agent) * RM_T + (int)threadIdx.x) * NB;
     const int B = bv.num_beams;
     int nlook = 0;
-    if (i < B) {
+    if (i0 < B) {
         double px, py, ti0;
         if (STANDALONE) {
             px = g.scan_pose[3 * (size_t)a];
@@ -185,36 +231,92 @@ __global__ void __launch_bounds__(RM_T) k_raymarch_cells(MapView m, BeamView bv,
             const double2 xy = __ldg(sp), yt = __ldg(sp + 1);
             px = xy.x; py = xy.y; ti0 = yt.y;
         }
-        const int ti = beam_theta_index(ti0, i, bv.theta_index_increment, m.theta_dis_f);
-        const double s = __ldg(m.sines + ti), c = __ldg(m.cosines + ti);
-        double range;
+        double range[NB];
         if (fabs(px) < 1e8 && fabs(py) < 1e8) {
             CellConsts k;
             k.ox = m.orig_x * m.inv_resolution; k.oy = m.orig_y * m.inv_resolution;
             k.eps = m.eps * m.inv_resolution; k.tmax = m.max_range * m.inv_resolution;
             k.width = (unsigned)m.width; k.height = (unsigned)m.height;
             k.last = (unsigned)m.width * (unsigned)m.height - 1u;
-            // pin the loop constants in registers (otherwise they are re-fetched from the constant bank
-            // with LDCU inside the march loop, costing issue slots)
-            asm volatile("" : "+d"(k.ox), "+d"(k.oy), "+d"(k.eps), "+d"(k.tmax));
-            asm volatile("" : "+r"(k.width), "+r"(k.height), "+r"(k.last));
-            const double T = trace_ray_cells<COUNT>(m.dt_cells, px * m.inv_resolution, py * m.inv_resolution, s, c, k, nlook);
-            range = ((T > k.tmax) ? k.tmax : T) * m.resolution;
+            const double *__restrict__ dtc = m.dt_cells;
+            const double X0 = px * m.inv_resolution, Y0 = py * m.inv_resolution;
+            double X[NB], Y[NB], S[NB], C[NB], D[NB], T[NB];
+            bool act[NB];
+            const unsigned idx00 = cell_index(X0, Y0, k);           // every beam starts in the pose cell
+            const double d0 = CODED ? coded_lookup(m, idx00) : __ldg(dtc + idx00);
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+                const int i = i0 + q;
+                const int ti = beam_theta_index(ti0, (i < B) ? i : (B - 1), bv.theta_index_increment, m.theta_dis_f);
+                S[q] = __ldg(m.sines + ti); C[q] = __ldg(m.cosines + ti);
+                X[q] = X0; Y[q] = Y0; D[q] = d0; T[q] = d0;
+                act[q] = (i < B) && (d0 > k.eps) && (d0 <= k.tmax);
+                if (COUNT && i < B) nlook++;
+            }
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < NB; q++) any = any || act[q];
+            while (any) {
+                unsigned idx[NB];
+#pragma unroll
+                for (int q = 0; q < NB; q++) {
+                    if (act[q]) { X[q] = X[q] + D[q] * C[q]; Y[q] = Y[q] + D[q] * S[q]; }
+                    idx[q] = cell_index(X[q], Y[q], k);
+                }
+#pragma unroll
+                for (int q = 0; q < NB; q++)
+                    if (act[q]) D[q] = CODED ? coded_lookup(m, idx[q]) : __ldg(dtc + idx[q]);
+                any = false;
+#pragma unroll
+                for (int q = 0; q < NB; q++) {
+                    if (act[q]) {
+                        T[q] = T[q] + D[q];
+                        if (COUNT) nlook++;
+                        act[q] = (D[q] > k.eps) && (T[q] <= k.tmax);
+                    }
+                    any = any || act[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; q++) range[q] = ((T[q] > k.tmax) ? k.tmax : T[q]) * m.resolution;
         } else {
-            range = trace_ray<false>(m, px, py, s, c, nlook);   // absurd coordinates: literal reference arithmetic
+#pragma unroll
+            for (int q = 0; q < NB; q++) {   // absurd coordinates: literal reference arithmetic
+                const int i = i0 + q;
+                int n1 = 0;
+                const int ti = beam_theta_index(ti0, (i < B) ? i : (B - 1), bv.theta_index_increment, m.theta_dis_f);
+                range[q] = trace_ray<false>(m, px, py, __ldg(m.sines + ti), __ldg(m.cosines + ti), n1);
+                if (COUNT && i < B) nlook += n1;
+            }
         }
-        if (g.noise_std > 0.0) {
-            unsigned long long tick = g.tick_counter ? *g.tick_counter : 0ull;
-            range = range + g.noise_std * normal_sample(g.noise_seed, tick, (uint64_t)a * (uint64_t)B + (uint64_t)i);
+        const double v = g.wall_flag ? __ldg(g.vel + a) : 0.0;
+        const unsigned long long tick = (g.noise_std > 0.0 && g.tick_counter) ? *g.tick_counter : 0ull;
+        bool hit = false;
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+            const int i = i0 + q;
+            if (i < B) {
+                double r = range[q];
+                if (g.noise_std > 0.0)
+                    r = r + g.noise_std * normal_sample(g.noise_seed, tick, (uint64_t)a * (uint64_t)B + (uint64_t)i);
+                if (g.wall_flag)
+                    hit = hit || ttc_hit(r, v, __ldg(bv.cosines + i), __ldg(bv.side_distances + i), g.ttc_thresh);
+                range[q] = r;
+            }
         }
-        if (g.wall_flag) {
-            const double v = __ldg(g.vel + a);
-            if (ttc_hit(range, v, __ldg(bv.cosines + i), __ldg(bv.side_distances + i), g.ttc_thresh))
-                atomicOr(g.wall_flag + a, 1);
+        if (hit) atomicOr(g.wall_flag + a, 1);
+        const size_t o = (size_t)a * (size_t)B + (size_t)i0;
+        if (NB == 2 && i0 + 1 < B && ((B & 1) == 0)) {
+            if (g.out_f32) *reinterpret_cast<float2 *>(g.out_f32 + o) = make_float2((float)range[0], (float)range[NB - 1]);
+            if (g.out_f64) *reinterpret_cast<double2 *>(g.out_f64 + o) = make_double2(range[0], range[NB - 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NB; q++)
+                if (i0 + q < B) {
+                    if (g.out_f32) g.out_f32[o + q] = (float)range[q];
+                    if (g.out_f64) g.out_f64[o + q] = range[q];
+                }
         }
-        const size_t o = (size_t)a * (size_t)B + (size_t)i;
-        if (g.out_f32) g.out_f32[o] = (float)range;
-        if (g.out_f64) g.out_f64[o] = range;
     }
     if (COUNT) {
         unsigned n = (unsigned)nlook;
@@ -293,11 +395,21 @@ __global__ void __launch_bounds__(128) k_finalize(f110_sim s, BeamView bv) {
             __syncwarp();
         }
     }
-    // tick counter: bumped once per f110_step by the last kernel of the tick
-    if (a == 0 && lane == 0 && s.tick_counter) *s.tick_counter += 1ull;
+    // tick counter: bumped once per f110_step by the last kernel of the tick; the march-hint list counters
+    // are consumed by now (k_march ran) and are refilled by the next tick's k_dynamics
+    if (a == 0 && lane == 0) {
+        if (s.tick_counter) *s.tick_counter += 1ull;
+        if (s.march_count) { s.march_count[0] = 0u; s.march_count[1] = 0u; s.march_count[2] = 0u; }
+    }
 }
 
 // ------------------------------------------------------------------------------------ reset kernels
+// a reset agent has no lookup history: its march items are scheduled with the very-heavy class next tick
+__device__ __forceinline__ void mark_march_cost_unknown(const f110_sim &s, size_t a) {
+    if (s.march_cost)
+        for (int j = 0; j < s.march_ipa; j++) s.march_cost[a * (size_t)s.march_ipa + j] = F110_Q_UNKNOWN;
+}
+
 __global__ void k_reset(f110_sim s, const double *__restrict__ poses, const uint8_t *__restrict__ mask) {
     const int NA = s.num_envs * s.num_agents;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,6 +425,7 @@ __global__ void k_reset(f110_sim s, const double *__restrict__ poses, const uint
     s.steer_buf[a] = 0.0;
     s.steer_buf[(size_t)NA + a] = 0.0;
     s.wall_flag[a] = 0;
+    mark_march_cost_unknown(s, a);
 }
 
 __device__ __forceinline__ void env_counters_reset(const f110_sim &s, int env, const double *agent_pose3 /* [A][3] */) {
@@ -407,6 +520,7 @@ __global__ void k_autoreset(f110_sim s, const double *__restrict__ start_poses, 
         s.steer_buf[a] = 0.0;
         s.steer_buf[(size_t)NA + a] = 0.0;
         s.wall_flag[a] = 0;
+        mark_march_cost_unknown(s, a);
     }
     if (s.current_time && A <= 32) env_counters_reset(s, env, pose3);
 }
@@ -531,19 +645,59 @@ static int check_beams(const f110_beams *b) {
     return F110_OK;
 }
 
+// variant selection for A/B measurements: F110_RM_VARIANT = "<beams per thread><min blocks/SM>" e.g. "1x24", "2x16"
+static unsigned long long *g_trace = nullptr;   // debug only: per-block timeline buffer (f110_debug_set_trace)
+
+static int num_sms() {
+    static int n = 0;
+    if (n <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+static int rm_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("F110_RM_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <int NB, int MINB, bool CODED>
+static void launch_cells(const MapView &mv, const BeamView &bv, const MarchArgs &g, bool standalone, bool count,
+                         unsigned blocks, int bpa, cudaStream_t st) {
+    if (standalone) {
+        if (count) k_raymarch_cells<true, true, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+        else k_raymarch_cells<true, false, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+    } else {
+        if (count) k_raymarch_cells<false, true, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+        else k_raymarch_cells<false, false, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+    }
+}
+
 static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArgs &g, bool fast, bool standalone,
                            cudaStream_t st) {
     if (fast && mv.dt_cells && (unsigned long long)mv.width * (unsigned long long)mv.height < (1ull << 32)) {
-        const int bpa = (bv.num_beams + RM_T - 1) / RM_T;
+        const int variant = rm_variant();
+        const int nb = (variant == 2 || variant == 3 || variant == 6) ? 2 : 1;
+        const int per_block = RM_T * nb;
+        const int bpa = (bv.num_beams + per_block - 1) / per_block;
         const long long blocks = (g.total / bv.num_beams) * bpa;
         if (blocks <= 0 || blocks > 0x7fffffffll) return F110_ERR_INVALID;
         const bool count = g.lookup_counter != nullptr;
-        if (standalone) {
-            if (count) k_raymarch_cells<true, true><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
-            else k_raymarch_cells<true, false><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
-        } else {
-            if (count) k_raymarch_cells<false, true><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
-            else k_raymarch_cells<false, false><<<(unsigned)blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
+        const bool coded = mv.dt_codes && mv.dt_lut;
+        switch (variant) {
+            case 1: launch_cells<1, 32, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
+            case 2: launch_cells<2, 1, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
+            case 3: launch_cells<2, 20, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
+            case 4: if (coded) { launch_cells<1, 1, true>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break; }
+            case 5: if (coded) { launch_cells<1, 32, true>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break; }
+            case 6: if (coded) { launch_cells<2, 1, true>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break; }
+            default: launch_cells<1, 1, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
         }
         LAUNCH_CHECK("k_raymarch_cells");
         return F110_OK;
@@ -557,6 +711,19 @@ static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArg
     return F110_OK;
 }
 
+template <int MINB>
+static void launch_march(const MarchK &k, dim3 grid, bool coded, bool noise, bool count, cudaStream_t st) {
+    if (coded) {
+        if (count) k_march<true, false, true, MINB><<<grid, 64, 0, st>>>(k);
+        else if (noise) k_march<true, true, false, MINB><<<grid, 64, 0, st>>>(k);
+        else k_march<true, false, false, MINB><<<grid, 64, 0, st>>>(k);
+    } else {
+        if (count) k_march<false, false, true, MINB><<<grid, 64, 0, st>>>(k);
+        else if (noise) k_march<false, true, false, MINB><<<grid, 64, 0, st>>>(k);
+        else k_march<false, false, false, MINB><<<grid, 64, 0, st>>>(k);
+    }
+}
+
 }  // namespace f110
 
 using namespace f110;
@@ -565,6 +732,10 @@ using namespace f110;
 extern "C" {
 
 int f110_abi_version(void) { return F110_ABI_VERSION; }
+
+/* debug aid (not in the public header): device buffer [blocks][4] u64 that the march kernels fill with
+ * (smid, start ns, end ns, max steps of warp 0) per block; NULL switches it off. */
+void f110_debug_set_trace(unsigned long long *buf) { g_trace = buf; }
 
 const char *f110_status_string(int status) {
     switch (status) {
@@ -591,10 +762,68 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     const BeamView bv = make_view(beams);
 
     if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
-    k_dynamics<<<(NA + 127) / 128, 128, 0, st>>>(*sim, actions, beams->fov, (double)map->theta_dis);
+    const int variant = rm_variant();
+    const bool queued = sim->march_cost && sim->march_order && sim->march_count && variant != 7 &&
+                        sim->march_ipa == (beams->num_beams + 31) / 32 && sim->march_ipa <= 256 &&
+                        (unsigned long long)NA * (unsigned)sim->march_ipa < (1ull << 24) * 256ull &&
+                        map->fast_path && map->dt_cells && map->sincos && beams->cos_side;
+    const int dyn_blocks = (NA + 127) / 128;
+    const int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 127) / 128) : 0;
+    k_dynamics<<<dyn_blocks + order_blocks, 128, 0, st>>>(*sim, actions, beams->fov, (double)map->theta_dis, dyn_blocks);
     LAUNCH_CHECK("k_dynamics");
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 
+    if (map->fast_path && map->dt_cells && map->sincos && beams->cos_side && variant < 10 &&
+        (unsigned long long)map->width * (unsigned long long)map->height < (1ull << 32)) {
+        MarchK k;
+        const bool coded = map->dt_codes && map->dt_lut && variant != 8;
+        k.codes = map->dt_codes; k.lut = map->dt_lut; k.cells = map->dt_cells;
+        k.sincos = reinterpret_cast<const double2 *>(map->sincos);
+        k.cos_side = reinterpret_cast<const double2 *>(beams->cos_side);
+        k.scan_pose = reinterpret_cast<const double2 *>(sim->scan_pose);
+        k.vel = sim->state + (size_t)3 * NA;
+        k.out = sim->scans; k.wall_flag = sim->wall_flag;
+        k.lookup_counter = sim->lookup_counter; k.tick_counter = sim->tick_counter;
+        k.inv_res = 1.0 / map->resolution; k.res = map->resolution;
+        k.ox = map->orig_x * k.inv_res; k.oy = map->orig_y * k.inv_res;
+        k.eps = map->eps * k.inv_res; k.tmax = map->max_range * k.inv_res;
+        k.inc = beams->theta_index_increment; k.theta_dis_f = (double)map->theta_dis;
+        k.ti_guard = 4.0 * ((double)beams->num_beams * 1.14e-13 + 1e-12);
+        k.ttc_thresh = sim->ttc_thresh; k.ttc_margin = sim->ttc_thresh * 1.000001;
+        k.noise_std = sim->noise_std; k.noise_seed = sim->noise_seed;
+        k.width = (unsigned)map->width; k.height = (unsigned)map->height;
+        k.last = (unsigned)map->width * (unsigned)map->height - 1u;
+        k.B = beams->num_beams;
+        k.trace = g_trace;
+        k.dt = map->dt; k.orig_x = map->orig_x; k.orig_y = map->orig_y; k.x_max = mv.x_max; k.y_max = mv.y_max;
+        k.dt_oob = map->dt_oob; k.eps_m = map->eps; k.max_range = map->max_range;
+        const int bpa = (beams->num_beams + 63) / 64;
+        if (bpa > 65000) return F110_ERR_INVALID;
+        const bool noise = sim->noise_std > 0.0, count = sim->lookup_counter != nullptr;
+        if (queued) {
+            MarchQueue mq;
+            mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
+            mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
+            const unsigned blocks = (unsigned)num_sms() * 4u;
+            if (coded) {
+                if (count) k_march_persistent<true, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else if (noise) k_march_persistent<true, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else k_march_persistent<true, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+            } else {
+                if (count) k_march_persistent<false, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else if (noise) k_march_persistent<false, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else k_march_persistent<false, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+            }
+        } else {
+            const dim3 grid((unsigned)NA, (unsigned)bpa);
+            if (variant == 9) launch_march<24>(k, grid, coded, noise, count, st);
+            else launch_march<32>(k, grid, coded, noise, count, st);
+        }
+        LAUNCH_CHECK("k_march");
+        if (count && noise) return F110_ERR_INVALID;   // counting runs are noise-free by construction
+        goto marched;
+    }
+    {
     MarchArgs g;
     g.scan_pose = sim->scan_pose;
     g.vel = sim->state + (size_t)3 * NA;
@@ -608,6 +837,8 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     g.noise_seed = sim->noise_seed;
     g.total = (long long)NA * beams->num_beams;
     if ((rc = launch_raymarch(mv, bv, g, map->fast_path != 0, false, st))) return rc;
+    }
+marched:
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 
     k_finalize<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv);

@@ -13,6 +13,8 @@ namespace f110 {
 struct MapView {
     const double *__restrict__ dt;
     const double *__restrict__ dt_cells;   // dt / resolution (cell units); fast path only, else NULL
+    const uint8_t *__restrict__ dt_codes;  // rank code of dt_cells per cell (255 = escape), or NULL
+    const double *__restrict__ dt_lut;     // [256] code -> dt_cells value (exact), entry 255 unused
     const double *__restrict__ sines;
     const double *__restrict__ cosines;
     double orig_x, orig_y, orig_c, orig_s, resolution, inv_resolution, x_max, y_max;
@@ -57,6 +59,18 @@ __device__ __forceinline__ double trace_ray_cells(const double *__restrict__ dtc
     }
     nlook = n;
     return T;
+}
+
+// Coded table: one BYTE per cell holding the rank of the cell's DT value among the 255 smallest
+// distinct values of the map (on example_map: every distance below 27.3 cells = 1.7 m, i.e. every
+// cell a ray from the track can touch), 255 = "escape: read the fp64 table".  Lossless by
+// construction.  A 32-byte sector now holds 32 cells instead of 4, so the per-scan footprint drops
+// from ~1300 to ~480 sectors and the march's dependent load becomes an L1 hit almost always; the
+// code -> fp64 lookup is a second, always-L1-resident 2 KB table.
+__device__ __forceinline__ double coded_lookup(const MapView &m, unsigned idx) {
+    const unsigned code = __ldg(m.dt_codes + idx);
+    if (code == 255u) return __ldg(m.dt_cells + idx);
+    return __ldg(m.dt_lut + code);
 }
 
 // laser_models.py:55-104 xy_2_rc + distance_transform.
@@ -111,15 +125,19 @@ __device__ __forceinline__ double theta_index0(double yaw, double fov, double th
 }
 
 // laser_models.py:175-184: the reference walks theta_index sequentially (`+= inc`, wrap at theta_dis).
-// Per-lane closed form ti0 + i*inc (mod theta_dis); the sequential fp64 value differs from it by
-// < 1e-9, so int() can only disagree when the fractional part is within 1e-6 of an integer — in that
-// (2e-6-probability) case the exact sequential recurrence is replayed for this beam.
-__device__ __forceinline__ int beam_theta_index(double ti0, int i, double inc, double theta_dis_f) {
+// Per-lane closed form ti0 + i*inc (mod theta_dis).  Every sequential add rounds by at most half an ulp
+// of a value < 2048 (1.14e-13) and the wrap subtraction is exact, so after i <= num_beams adds the
+// sequential value is within num_beams * 1.14e-13 of the closed form (2.5e-10 for 2160 beams): int() can
+// only disagree when the fractional part is within `guard` (host: 4 * that bound) of an integer, and in
+// that rare case (~1e-9 per beam; the replay costs up to ~20 us on one lane, so it must stay rare) the
+// exact sequential recurrence is replayed for this beam.
+__device__ __forceinline__ int beam_theta_index(double ti0, int i, double inc, double theta_dis_f,
+                                                double guard = 1e-6) {
     double v = ti0 + (double)i * inc;
     while (v >= theta_dis_f) v -= theta_dis_f;
     int iv = (int)v;
     double fr = v - (double)iv;
-    if (fr < 1e-6 || fr > 1.0 - 1e-6) {
+    if (fr < guard || fr > 1.0 - guard) {
         double t = ti0;
         for (int k = 0; k < i; k++) {
             t += inc;

@@ -52,6 +52,20 @@ class HostMap(object):
         self.fast_path = int(m == 0.5 and self.orig_c == 1.0 and self.orig_s == 0.0)
 
 
+def code_table(values, ncodes=255):
+    """Lossless byte coding of a DT grid: code = rank of the cell value among the `ncodes` smallest distinct
+    values, 255 = escape.  Returns (codes uint8 [H,W], lut float64 [256]); lut[code] == value bit-exactly."""
+    uniq = np.unique(values)
+    small = uniq[:ncodes]
+    lut = np.full((256,), np.nan)
+    lut[:small.size] = small
+    pos = np.searchsorted(small, values)
+    pos_c = np.minimum(pos, small.size - 1)
+    exact = (pos < small.size) & (small[pos_c] == values)
+    codes = np.where(exact, pos_c, 255).astype(np.uint8)
+    return np.ascontiguousarray(codes), lut
+
+
 def load_map(map_path, map_ext):
     import yaml
     from PIL import Image

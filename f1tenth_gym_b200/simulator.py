@@ -43,13 +43,21 @@ class DeviceMap(object):
         sines, cosines = hostmaps.angle_lut(theta_dis)
         self.dt = torch.from_numpy(host_map.dt).to(device)
         # cell-unit copy for the fast path (res = 2^-k: the division is an exact exponent shift)
-        self.dt_cells = torch.from_numpy(host_map.dt / host_map.resolution).to(device) if host_map.fast_path else None
+        self.dt_cells = self.dt_codes = self.dt_lut = None
+        if host_map.fast_path:
+            cells = host_map.dt / host_map.resolution
+            codes, lut = hostmaps.code_table(cells)
+            self.dt_cells = torch.from_numpy(cells).to(device)
+            self.dt_codes = torch.from_numpy(codes).to(device)
+            self.dt_lut = torch.from_numpy(lut).to(device)
         self.sines = torch.from_numpy(sines).to(device)
         self.cosines = torch.from_numpy(cosines).to(device)
+        self.sincos = torch.from_numpy(np.ascontiguousarray(np.stack([sines, cosines], axis=1))).to(device)
         self.c = nat.F110Map(host_map.height, host_map.width, host_map.resolution, host_map.orig_x,
                              host_map.orig_y, host_map.orig_c, host_map.orig_s, eps, max_range, theta_dis,
                              host_map.fast_path, host_map.dt_oob, nat.ptr(self.dt), nat.ptr(self.dt_cells),
-                             nat.ptr(self.sines), nat.ptr(self.cosines))
+                             nat.ptr(self.dt_codes), nat.ptr(self.dt_lut), nat.ptr(self.sines), nat.ptr(self.cosines),
+                             nat.ptr(self.sincos))
 
     @classmethod
     def from_yaml(cls, map_path, map_ext, device, **kw):
@@ -65,10 +73,12 @@ class DeviceBeams(object):
         self.scan_angles = torch.from_numpy(sa).to(device)
         self.cosines = torch.from_numpy(co).to(device)
         self.side_distances = torch.from_numpy(sd).to(device)
+        self.cos_side = torch.from_numpy(np.ascontiguousarray(np.stack([co, sd], axis=1))).to(device)
         self.angle_increment = fov / (num_beams - 1)
         self.c = nat.F110Beams(num_beams, fov, self.angle_increment,
                                hostmaps.theta_index_increment(num_beams, fov, theta_dis),
-                               nat.ptr(self.scan_angles), nat.ptr(self.cosines), nat.ptr(self.side_distances))
+                               nat.ptr(self.scan_angles), nat.ptr(self.cosines), nat.ptr(self.side_distances),
+                               nat.ptr(self.cos_side))
 
 
 def empty_map_struct():
@@ -85,7 +95,7 @@ class Simulator(object):
 
     def __init__(self, params, num_agents, seed, time_step=0.01, ego_idx=0, integrator=Integrator.RK4,
                  lidar_dist=0.0, num_envs=1, num_beams=1080, fov=4.7, device=None, noise_std=0.0,
-                 count_lookups=False):
+                 count_lookups=False, march_queue=True):
         nat.lib()   # fail loudly right away if the CUDA library is missing
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
@@ -135,6 +145,12 @@ class Simulator(object):
         self.checkpoint_done = torch.zeros((NA,), dtype=torch.uint8, device=dev)
         self.lookup_counter = torch.zeros((1,), dtype=torch.int64, device=dev) if count_lookups else None
         self.tick_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
+        # work queue of the persistent ray-march kernel (csrc/march.cuh): last tick's heavy items go first
+        self.march_ipa = (B + 31) // 32 if (march_queue and (B + 31) // 32 <= 256) else 0
+        items = NA * self.march_ipa
+        self.march_cost = torch.full((items,), -1, **i32) if self.march_ipa else None
+        self.march_order = torch.zeros((3, items), **i32) if self.march_ipa else None
+        self.march_count = torch.zeros((4,), **i32) if self.march_ipa else None
         self.beams = DeviceBeams(num_beams, fov, params, dev)
         self.map = None
         self._map_struct = empty_map_struct()
@@ -148,6 +164,7 @@ class Simulator(object):
             nat.ptr(self.near_starts), nat.ptr(self.start_xs), nat.ptr(self.start_ys),
             nat.ptr(self.start_thetas), nat.ptr(self.start_rot), nat.ptr(self.done),
             nat.ptr(self.checkpoint_done), nat.ptr(self.lookup_counter), nat.ptr(self.tick_counter),
+            nat.ptr(self.march_cost), nat.ptr(self.march_order), nat.ptr(self.march_count), self.march_ipa,
             float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
         self._graph = None
 

@@ -52,7 +52,11 @@ typedef struct {
     const double *dt;               /* [height*width] fp64 distance transform, row 0 = image bottom */
     const double *dt_cells;         /* [height*width] dt / resolution (exact when fast_path), or NULL: enables
                                        the cell-unit march; ignored unless fast_path */
+    const uint8_t *dt_codes;        /* [height*width] rank of dt_cells among the map's 255 smallest distinct values,
+                                       255 = escape (read dt_cells); NULL disables the coded march */
+    const double *dt_lut;           /* [256] code -> dt_cells value (bit-exact) */
     const double *sines, *cosines;  /* [theta_dis]  sin/cos(linspace(0, 2pi, theta_dis)) (:379-381) */
+    const double *sincos;           /* [theta_dis][2] the same values interleaved (sin, cos), or NULL */
 } f110_map;
 
 /* Beam tables RaceCar.__init__ builds once (base_classes.py:122-158) + ScanSimulator2D.__init__ (:360-368). */
@@ -60,6 +64,7 @@ typedef struct {
     int32_t num_beams;
     double fov, angle_increment, theta_index_increment;
     const double *scan_angles, *cosines, *side_distances;   /* [num_beams] */
+    const double *cos_side;         /* [num_beams][2] (cosines[i], side_distances[i]) interleaved, or NULL */
 } f110_beams;
 
 /* Simulator / RaceCar / F110Env state for N envs x A agents, SoA, caller-owned device memory. */
@@ -90,6 +95,13 @@ typedef struct {
     unsigned long long *lookup_counter;   /* optional [1]: total DT lookups (roofline denominator); NULL = off */
     unsigned long long *tick_counter;     /* optional [1]: incremented by every f110_step; keys the noise stream
                                              and the auto-reset draw so that CUDA-graph replays stay distinct */
+    /* optional work queue of the persistent ray-march kernel (csrc/march.cuh): 32-beam items, last tick's
+       heavy items first.  Results never depend on it.  All NULL/0 = off (one block per 64-beam tile instead).
+       I = N*A*march_ipa items, march_ipa = ceil(num_beams/32) <= 256. */
+    uint32_t *march_cost;           /* [I]     initialised to 0xFFFFFFFF (= unknown) by the caller */
+    uint32_t *march_order;          /* [3][I]  */
+    uint32_t *march_count;          /* [4]     zero-initialised by the caller */
+    int32_t march_ipa;
     /* scan noise (laser_models.py:429,450-452): N(0, noise_std^2) per beam, added before iTTC; 0 = off */
     double noise_std;
     uint64_t noise_seed;

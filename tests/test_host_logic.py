@@ -48,6 +48,30 @@ def test_map_pipeline_matches_oracle_and_flags():
     assert maps.resolve_map_path('/tmp/custom') == '/tmp/custom.yaml'      # f110_env.py:117-118
 
 
+def test_device_tables_construct_on_cpu():
+    """DeviceMap / DeviceBeams only allocate and fill tensors: build them on the CPU device to check the
+    struct wiring (field order, derived tables) without a GPU."""
+    import torch
+    from f1tenth_gym_b200 import maps
+    from f1tenth_gym_b200.simulator import DeviceBeams, DeviceMap
+    hm = maps.load_map(maps.resolve_map_path('example_map'), '.png')
+    dm = DeviceMap(hm, torch.device('cpu'))
+    assert dm.c.fast_path == 1 and dm.c.dt_codes and dm.c.dt_lut and dm.c.dt_cells and dm.c.sincos
+    codes, lut = dm.dt_codes.numpy(), dm.dt_lut.numpy()
+    cells = dm.dt_cells.numpy()
+    ok = codes != 255
+    assert ok.any() and np.array_equal(lut[codes[ok]], cells[ok])         # lossless coding
+    assert np.array_equal(cells * hm.resolution, hm.dt)                  # exact power-of-two scaling
+    assert (cells[~ok] > lut[254]).all()
+    assert np.array_equal(dm.sincos.numpy()[:, 0], dm.sines.numpy())
+    db = DeviceBeams(1080, 4.7, maps.DEFAULT_PARAMS, torch.device('cpu'))
+    assert np.array_equal(db.cos_side.numpy()[:, 1], db.side_distances.numpy())
+    assert db.c.num_beams == 1080 and db.c.cos_side
+    hb = maps.load_map(maps.resolve_map_path('berlin'), '.png')
+    dmb = DeviceMap(hb, torch.device('cpu'))
+    assert dmb.c.fast_path == 0 and not dmb.c.dt_codes and not dmb.c.dt_cells
+
+
 def declared_symbols():
     txt = open(HEADER).read()
     txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)

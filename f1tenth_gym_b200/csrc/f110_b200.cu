@@ -77,14 +77,14 @@ __device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned w,
     if (w < items) {
         const unsigned ipa = (unsigned)s.march_ipa;
         const unsigned a = w / ipa, j = w - a * ipa;
-        const unsigned c = s.march_cost[w];
+        packed = (a << 8) | j;
+        const unsigned c = s.march_cost[packed];
         unsigned m = c;
         if (c != F110_Q_UNKNOWN) {
-            if (j > 0) { const unsigned cl = s.march_cost[w - 1]; if (cl != F110_Q_UNKNOWN) m = max(m, cl); }
-            if (j + 1 < ipa) { const unsigned cr = s.march_cost[w + 1]; if (cr != F110_Q_UNKNOWN) m = max(m, cr); }
+            if (j > 0) { const unsigned cl = s.march_cost[packed - 1]; if (cl != F110_Q_UNKNOWN) m = max(m, cl); }
+            if (j + 1 < ipa) { const unsigned cr = s.march_cost[packed + 1]; if (cr != F110_Q_UNKNOWN) m = max(m, cr); }
         }
         cls = (c == F110_Q_UNKNOWN || c >= F110_Q_VERY_HEAVY) ? 0 : (m >= F110_Q_HEAVY) ? 1 : 2;
-        packed = (a << 8) | j;
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -205,127 +205,6 @@ __global__ void __launch_bounds__(256) k_raymarch(MapView m, BeamView bv, MarchA
     }
 }
 
-// ------------------------------------------------------------------------------------ k_raymarch_cells
-// Fast path (power-of-two resolution, unrotated origin): RM_T-thread blocks, each block owns RM_T
-// consecutive beams of ONE agent (17 blocks of 64 cover 1080 beams with 0.7 % padding), so the pose is
-// block-uniform, the lanes of a warp walk neighbouring DT cells, and the block scheduler balances load
-// at a 64-beam granularity.  See lidar.cuh for the cell-unit march.
-#define RM_T 64
-// NB beams per thread (adjacent beams i, i+1: strongly correlated step counts) give NB independent
-// dependent-load chains per lane: the march is latency-bound (long-scoreboard stalls dominate), so
-// memory-level parallelism per warp matters more than instruction count.
-template <bool STANDALONE, bool COUNT, int NB, int MINB, bool CODED>
-__global__ void __launch_bounds__(RM_T, MINB) k_raymarch_cells(MapView m, BeamView bv, MarchArgs g, int blocks_per_agent) {
-    const unsigned a = blockIdx.x / (unsigned)blocks_per_agent;
-    const int i0 = ((int)(blockIdx.x - a * (unsigned)blocks_per_agent) * RM_T + (int)threadIdx.x) * NB;
-    const int B = bv.num_beams;
-    int nlook = 0;
-    if (i0 < B) {
-        double px, py, ti0;
-        if (STANDALONE) {
-            px = g.scan_pose[3 * (size_t)a];
-            py = g.scan_pose[3 * (size_t)a + 1];
-            ti0 = theta_index0(g.scan_pose[3 * (size_t)a + 2], bv.fov, m.theta_dis_f);
-        } else {
-            const double2 *sp = reinterpret_cast<const double2 *>(g.scan_pose) + 2 * (size_t)a;
-            const double2 xy = __ldg(sp), yt = __ldg(sp + 1);
-            px = xy.x; py = xy.y; ti0 = yt.y;
-        }
-        double range[NB];
-        if (fabs(px) < 1e8 && fabs(py) < 1e8) {
-            CellConsts k;
-            k.ox = m.orig_x * m.inv_resolution; k.oy = m.orig_y * m.inv_resolution;
-            k.eps = m.eps * m.inv_resolution; k.tmax = m.max_range * m.inv_resolution;
-            k.width = (unsigned)m.width; k.height = (unsigned)m.height;
-            k.last = (unsigned)m.width * (unsigned)m.height - 1u;
-            const double *__restrict__ dtc = m.dt_cells;
-            const double X0 = px * m.inv_resolution, Y0 = py * m.inv_resolution;
-            double X[NB], Y[NB], S[NB], C[NB], D[NB], T[NB];
-            bool act[NB];
-            const unsigned idx00 = cell_index(X0, Y0, k);           // every beam starts in the pose cell
-            const double d0 = CODED ? coded_lookup(m, idx00) : __ldg(dtc + idx00);
-#pragma unroll
-            for (int q = 0; q < NB; q++) {
-                const int i = i0 + q;
-                const int ti = beam_theta_index(ti0, (i < B) ? i : (B - 1), bv.theta_index_increment, m.theta_dis_f);
-                S[q] = __ldg(m.sines + ti); C[q] = __ldg(m.cosines + ti);
-                X[q] = X0; Y[q] = Y0; D[q] = d0; T[q] = d0;
-                act[q] = (i < B) && (d0 > k.eps) && (d0 <= k.tmax);
-                if (COUNT && i < B) nlook++;
-            }
-            bool any = false;
-#pragma unroll
-            for (int q = 0; q < NB; q++) any = any || act[q];
-            while (any) {
-                unsigned idx[NB];
-#pragma unroll
-                for (int q = 0; q < NB; q++) {
-                    if (act[q]) { X[q] = X[q] + D[q] * C[q]; Y[q] = Y[q] + D[q] * S[q]; }
-                    idx[q] = cell_index(X[q], Y[q], k);
-                }
-#pragma unroll
-                for (int q = 0; q < NB; q++)
-                    if (act[q]) D[q] = CODED ? coded_lookup(m, idx[q]) : __ldg(dtc + idx[q]);
-                any = false;
-#pragma unroll
-                for (int q = 0; q < NB; q++) {
-                    if (act[q]) {
-                        T[q] = T[q] + D[q];
-                        if (COUNT) nlook++;
-                        act[q] = (D[q] > k.eps) && (T[q] <= k.tmax);
-                    }
-                    any = any || act[q];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NB; q++) range[q] = ((T[q] > k.tmax) ? k.tmax : T[q]) * m.resolution;
-        } else {
-#pragma unroll
-            for (int q = 0; q < NB; q++) {   // absurd coordinates: literal reference arithmetic
-                const int i = i0 + q;
-                int n1 = 0;
-                const int ti = beam_theta_index(ti0, (i < B) ? i : (B - 1), bv.theta_index_increment, m.theta_dis_f);
-                range[q] = trace_ray<false>(m, px, py, __ldg(m.sines + ti), __ldg(m.cosines + ti), n1);
-                if (COUNT && i < B) nlook += n1;
-            }
-        }
-        const double v = g.wall_flag ? __ldg(g.vel + a) : 0.0;
-        const unsigned long long tick = (g.noise_std > 0.0 && g.tick_counter) ? *g.tick_counter : 0ull;
-        bool hit = false;
-#pragma unroll
-        for (int q = 0; q < NB; q++) {
-            const int i = i0 + q;
-            if (i < B) {
-                double r = range[q];
-                if (g.noise_std > 0.0)
-                    r = r + g.noise_std * normal_sample(g.noise_seed, tick, (uint64_t)a * (uint64_t)B + (uint64_t)i);
-                if (g.wall_flag)
-                    hit = hit || ttc_hit(r, v, __ldg(bv.cosines + i), __ldg(bv.side_distances + i), g.ttc_thresh);
-                range[q] = r;
-            }
-        }
-        if (hit) atomicOr(g.wall_flag + a, 1);
-        const size_t o = (size_t)a * (size_t)B + (size_t)i0;
-        if (NB == 2 && i0 + 1 < B && ((B & 1) == 0)) {
-            if (g.out_f32) *reinterpret_cast<float2 *>(g.out_f32 + o) = make_float2((float)range[0], (float)range[NB - 1]);
-            if (g.out_f64) *reinterpret_cast<double2 *>(g.out_f64 + o) = make_double2(range[0], range[NB - 1]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < NB; q++)
-                if (i0 + q < B) {
-                    if (g.out_f32) g.out_f32[o + q] = (float)range[q];
-                    if (g.out_f64) g.out_f64[o + q] = range[q];
-                }
-        }
-    }
-    if (COUNT) {
-        unsigned n = (unsigned)nlook;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-        if ((threadIdx.x & 31) == 0 && n) atomicAdd(g.lookup_counter, (unsigned long long)n);
-    }
-}
-
 // ------------------------------------------------------------------------------------ k_finalize
 // Warp per agent (base_classes.py:536-550 check_collision, :579-589 update_scan loop).
 __global__ void __launch_bounds__(128) k_finalize(f110_sim s, BeamView bv) {
@@ -407,7 +286,7 @@ __global__ void __launch_bounds__(128) k_finalize(f110_sim s, BeamView bv) {
 // a reset agent has no lookup history: its march items are scheduled with the very-heavy class next tick
 __device__ __forceinline__ void mark_march_cost_unknown(const f110_sim &s, size_t a) {
     if (s.march_cost)
-        for (int j = 0; j < s.march_ipa; j++) s.march_cost[a * (size_t)s.march_ipa + j] = F110_Q_UNKNOWN;
+        for (int j = 0; j < s.march_ipa; j++) s.march_cost[(a << 8) + (size_t)j] = F110_Q_UNKNOWN;
 }
 
 __global__ void k_reset(f110_sim s, const double *__restrict__ poses, const uint8_t *__restrict__ mask) {
@@ -645,7 +524,6 @@ static int check_beams(const f110_beams *b) {
     return F110_OK;
 }
 
-// variant selection for A/B measurements: F110_RM_VARIANT = "<beams per thread><min blocks/SM>" e.g. "1x24", "2x16"
 static unsigned long long *g_trace = nullptr;   // debug only: per-block timeline buffer (f110_debug_set_trace)
 
 static int num_sms() {
@@ -658,55 +536,29 @@ static int num_sms() {
     return n;
 }
 
+// A/B switch for measurements (profiles/): F110_MARCH_VARIANT = 0 default (persistent queue, fp64 cell table),
+// 6 = rank-coded byte table, 7 = no queue (one block per 64-beam tile), 9 = no queue, 40 registers
 static int rm_variant() {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("F110_RM_VARIANT");
+        const char *e = getenv("F110_MARCH_VARIANT");
         v = e ? atoi(e) : 0;
     }
     return v;
 }
 
-template <int NB, int MINB, bool CODED>
-static void launch_cells(const MapView &mv, const BeamView &bv, const MarchArgs &g, bool standalone, bool count,
-                         unsigned blocks, int bpa, cudaStream_t st) {
-    if (standalone) {
-        if (count) k_raymarch_cells<true, true, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
-        else k_raymarch_cells<true, false, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
-    } else {
-        if (count) k_raymarch_cells<false, true, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
-        else k_raymarch_cells<false, false, NB, MINB, CODED><<<blocks, RM_T, 0, st>>>(mv, bv, g, bpa);
-    }
-}
-
 static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArgs &g, bool fast, bool standalone,
                            cudaStream_t st) {
-    if (fast && mv.dt_cells && (unsigned long long)mv.width * (unsigned long long)mv.height < (1ull << 32)) {
-        const int variant = rm_variant();
-        const int nb = (variant == 2 || variant == 3 || variant == 6) ? 2 : 1;
-        const int per_block = RM_T * nb;
-        const int bpa = (bv.num_beams + per_block - 1) / per_block;
-        const long long blocks = (g.total / bv.num_beams) * bpa;
-        if (blocks <= 0 || blocks > 0x7fffffffll) return F110_ERR_INVALID;
-        const bool count = g.lookup_counter != nullptr;
-        const bool coded = mv.dt_codes && mv.dt_lut;
-        switch (variant) {
-            case 1: launch_cells<1, 32, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
-            case 2: launch_cells<2, 1, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
-            case 3: launch_cells<2, 20, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
-            case 4: if (coded) { launch_cells<1, 1, true>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break; }
-            case 5: if (coded) { launch_cells<1, 32, true>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break; }
-            case 6: if (coded) { launch_cells<2, 1, true>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break; }
-            default: launch_cells<1, 1, false>(mv, bv, g, standalone, count, (unsigned)blocks, bpa, st); break;
-        }
-        LAUNCH_CHECK("k_raymarch_cells");
-        return F110_OK;
-    }
     const int threads = 256;
     const long long blocks = (g.total + threads - 1) / threads;
     if (blocks <= 0 || blocks > 0x7fffffffll) return F110_ERR_INVALID;
-    if (standalone) k_raymarch<false, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
-    else k_raymarch<false, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+    if (fast) {
+        if (standalone) k_raymarch<true, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+        else k_raymarch<true, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+    } else {
+        if (standalone) k_raymarch<false, true><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+        else k_raymarch<false, false><<<(unsigned)blocks, threads, 0, st>>>(mv, bv, g);
+    }
     LAUNCH_CHECK("k_raymarch");
     return F110_OK;
 }
@@ -765,7 +617,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     const int variant = rm_variant();
     const bool queued = sim->march_cost && sim->march_order && sim->march_count && variant != 7 &&
                         sim->march_ipa == (beams->num_beams + 31) / 32 && sim->march_ipa <= 256 &&
-                        (unsigned long long)NA * (unsigned)sim->march_ipa < (1ull << 24) * 256ull &&
+                        (unsigned long long)NA < (1ull << 22) &&
                         map->fast_path && map->dt_cells && map->sincos && beams->cos_side;
     const int dyn_blocks = (NA + 127) / 128;
     const int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 127) / 128) : 0;
@@ -773,10 +625,10 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     LAUNCH_CHECK("k_dynamics");
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 
-    if (map->fast_path && map->dt_cells && map->sincos && beams->cos_side && variant < 10 &&
+    if (map->fast_path && map->dt_cells && map->sincos && beams->cos_side && true &&
         (unsigned long long)map->width * (unsigned long long)map->height < (1ull << 32)) {
         MarchK k;
-        const bool coded = map->dt_codes && map->dt_lut && variant != 8;
+        const bool coded = map->dt_codes && map->dt_lut && variant == 6;   // measured: the fp64 table wins once issue-bound
         k.codes = map->dt_codes; k.lut = map->dt_lut; k.cells = map->dt_cells;
         k.sincos = reinterpret_cast<const double2 *>(map->sincos);
         k.cos_side = reinterpret_cast<const double2 *>(beams->cos_side);
@@ -805,14 +657,17 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
             const unsigned blocks = (unsigned)num_sms() * 4u;
-            if (coded) {
-                if (count) k_march_persistent<true, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else if (noise) k_march_persistent<true, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else k_march_persistent<true, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+            if (k.trace) {
+                if (coded) k_march_persistent<true, false, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else k_march_persistent<false, false, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+            } else if (coded) {
+                if (count) k_march_persistent<true, false, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else if (noise) k_march_persistent<true, true, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else k_march_persistent<true, false, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
             } else {
-                if (count) k_march_persistent<false, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else if (noise) k_march_persistent<false, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else k_march_persistent<false, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                if (count) k_march_persistent<false, false, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else if (noise) k_march_persistent<false, true, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
+                else k_march_persistent<false, false, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
             }
         } else {
             const dim3 grid((unsigned)NA, (unsigned)bpa);

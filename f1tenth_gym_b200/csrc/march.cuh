@@ -82,27 +82,31 @@ __device__ __noinline__ double escape_load(const double *__restrict__ cells, uns
 #define F110_Q_VERY_HEAVY 64u
 #define F110_Q_UNKNOWN 0xFFFFFFFFu
 struct MarchQueue {
-    unsigned *__restrict__ cost;            // [items] max lookups of the item in the last tick
+    unsigned *__restrict__ cost;            // [M << 8] max lookups of the item in the last tick, by packed id
     const unsigned *__restrict__ order;     // [3][items] class lists of packed items (agent << 8 | slice)
     const unsigned *__restrict__ count;     // [3]
     unsigned items;                         // M * ipa
     unsigned ipa;                           // 32-beam slices per agent (<= 256)
 };
 
+// One beam: LUT heading, sphere tracing in cell units, optional noise, iTTC predicate, fp32 range out.
+// xy = scan position (m), ti0 = LUT index of beam 0, v = longitudinal velocity of the agent.
 template <bool CODED, bool NOISE>
-__device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, unsigned &nlook) {
-    const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
-    const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
-    const int ti = beam_theta_index(yt.y, i, p.inc, p.theta_dis_f, p.ti_guard);
+__device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, double2 xy, double ti0, double v,
+                                           unsigned &nlook) {
+    const int ti = beam_theta_index(ti0, i, p.inc, p.theta_dis_f, p.ti_guard);
     const double2 sc = __ldg(p.sincos + ti);
     double range;
     unsigned n = 0;
     if (fabs(xy.x) < 1e8 && fabs(xy.y) < 1e8) {
         const double MAGIC = 6755399441055744.0;   // 2^52 + 2^51: round-down add == floor in the low word
-        double X = xy.x * p.inv_res, Y = xy.y * p.inv_res, T = 0.0, D;
-        const double *lut = p.lut;
-        asm volatile("" : "+l"(lut));   // keep in a register: no constant-bank reload in the loop
-        for (;;) {
+        // T and D start at 0 so that the first pass of the loop is the pose-cell lookup (X + 0*c == X and
+        // 0 + D == D exactly): one loop body, no peeled copy of it in the instruction stream
+        double X = xy.x * p.inv_res, Y = xy.y * p.inv_res, T = 0.0, D = 0.0;
+#pragma unroll 1
+        do {
+            X = X + D * sc.y;
+            Y = Y + D * sc.x;
             const int c = __double2loint(__dadd_rd(X - p.ox, MAGIC));
             const int r = __double2loint(__dadd_rd(Y - p.oy, MAGIC));
             unsigned idx = (unsigned)r * p.width + (unsigned)c;
@@ -110,16 +114,13 @@ __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, u
             if (CODED) {
                 const unsigned code = __ldg(p.codes + idx);
                 if (code == 255u) D = escape_load(p.cells, idx);
-                else D = __ldg(lut + code);
+                else D = __ldg(p.lut + code);
             } else {
                 D = __ldg(p.cells + idx);
             }
             T = T + D;
             n++;
-            if (!(D > p.eps && T <= p.tmax)) break;
-            X = X + D * sc.y;
-            Y = Y + D * sc.x;
-        }
+        } while (D > p.eps && T <= p.tmax);
         range = ((T > p.tmax) ? p.tmax : T) * p.res;
     } else {
         range = march_generic(p.dt, p.orig_x, p.orig_y, p.x_max, p.y_max, p.res, p.dt_oob, p.eps_m, p.max_range,
@@ -131,9 +132,8 @@ __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, u
         const unsigned long long tick = p.tick_counter ? *p.tick_counter : 0ull;
         range = range + p.noise_std * normal_sample(p.noise_seed, tick, (uint64_t)a * (uint64_t)p.B + (uint64_t)i);
     }
-    // check_ttc_jit, one beam: hit iff 0 <= fl(a/pv) < thresh.  |a| <= margin*|pv| is a necessary condition,
+    // check_ttc_jit, one beam: hit iff 0 <= fl(d/pv) < thresh.  |d| <= margin*|pv| is a necessary condition,
     // so the exact IEEE division only runs for beams that are about to touch a wall.
-    const double v = __ldg(p.vel + a);
     if (v != 0.0) {
         const double2 cs = __ldg(p.cos_side + i);
         const double pv = v * cs.x;
@@ -155,7 +155,11 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
     const int i = (int)(blockIdx.y * 64u + threadIdx.x);
     if (i >= p.B) return;
     unsigned nlook;
-    march_beam<CODED, NOISE>(p, a, i, nlook);
+    {
+        const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
+        const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
+        march_beam<CODED, NOISE>(p, a, i, xy, yt.y, __ldg(p.vel + a), nlook);
+    }
     if (p.trace || COUNT) {
         const unsigned act = __activemask();
         if (p.trace) {
@@ -172,37 +176,39 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
     }
 }
 
-// persistent: gridDim.x blocks of 512 threads stay resident; queue position q = k * gridDim.x + blockIdx.x
+// persistent: gridDim.x blocks of 512 threads stay resident; queue position q = k * gridDim.x + blockIdx.x.
+// cost[] is indexed by the packed item id (agent << 8 | slice), so no multiply/divide is needed per item.
 #define F110_MARCH_PT 512
-template <bool CODED, bool NOISE, bool COUNT>
+template <bool CODED, bool NOISE, bool COUNT, bool TRACE>
 __global__ void __launch_bounds__(F110_MARCH_PT, 4) k_march_persistent(const MarchK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
     if (threadIdx.x == 0) s_next = 0u;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nA = min(mq.count[0], mq.items), nB = min(mq.count[1], mq.items);
-    const unsigned total = min(nA + nB + min(mq.count[2], mq.items), mq.items);
-    unsigned long long looks = 0ull;
+    const unsigned nAB = nA + nB;
+    const unsigned total = min(nAB + min(mq.count[2], mq.items), mq.items);
+    unsigned looks = 0u;
     for (;;) {
         unsigned k = 0;
         if (lane == 0) k = atomicAdd(&s_next, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
-        const unsigned long long q = (unsigned long long)k * gridDim.x + blockIdx.x;
+        const unsigned q = k * gridDim.x + blockIdx.x;      // items < 2^32 / 4 (host-checked): no overflow
         if (q >= total) break;
         unsigned long long t0 = 0;
-        if (p.trace) t0 = gtime();
-        const unsigned qq = (unsigned)q;
-        const unsigned it = (qq < nA) ? mq.order[qq]
-                          : (qq < nA + nB) ? mq.order[(size_t)mq.items + (qq - nA)]
-                                           : mq.order[2 * (size_t)mq.items + (qq - nA - nB)];
-        const unsigned a = it >> 8, j = it & 255u;
-        const int i = (int)(j * 32u + lane);
+        if (TRACE) t0 = gtime();
+        const unsigned it = mq.order[(q < nA) ? q : (q < nAB) ? (mq.items + (q - nA)) : (2u * mq.items + (q - nAB))];
+        const unsigned a = it >> 8;
+        const int i = (int)((it & 255u) * 32u + lane);
+        const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
+        const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
+        const double v = __ldg(p.vel + a);
         unsigned nlook = 0;
-        if (i < p.B) march_beam<CODED, NOISE>(p, a, i, nlook);
+        if (i < p.B) march_beam<CODED, NOISE>(p, a, i, xy, yt.y, v, nlook);
         const unsigned mx = __reduce_max_sync(0xffffffffu, nlook);
         if (lane == 0) {
-            mq.cost[(size_t)a * mq.ipa + j] = mx;
-            if (p.trace) {
+            mq.cost[it] = mx;
+            if (TRACE) {
                 unsigned long long *tr = p.trace + 4ull * q;
                 tr[0] = smid(); tr[1] = t0; tr[2] = gtime(); tr[3] = mx;
             }
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(F110_MARCH_PT, 4) k_march_persistent(const Mar
         if (COUNT) looks += nlook;
     }
     if (COUNT) {
-        const unsigned n = __reduce_add_sync(0xffffffffu, (unsigned)looks);
+        const unsigned n = __reduce_add_sync(0xffffffffu, looks);
         if (lane == 0 && n) atomicAdd(p.lookup_counter, (unsigned long long)n);
     }
 }

@@ -148,7 +148,7 @@ class Simulator(object):
         # work queue of the persistent ray-march kernel (csrc/march.cuh): last tick's heavy items go first
         self.march_ipa = (B + 31) // 32 if (march_queue and (B + 31) // 32 <= 256) else 0
         items = NA * self.march_ipa
-        self.march_cost = torch.full((items,), -1, **i32) if self.march_ipa else None
+        self.march_cost = torch.full((NA * 256,), -1, **i32) if self.march_ipa else None
         self.march_order = torch.zeros((3, items), **i32) if self.march_ipa else None
         self.march_count = torch.zeros((4,), **i32) if self.march_ipa else None
         self.beams = DeviceBeams(num_beams, fov, params, dev)

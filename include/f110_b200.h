@@ -98,7 +98,7 @@ typedef struct {
     /* optional work queue of the persistent ray-march kernel (csrc/march.cuh): 32-beam items, last tick's
        heavy items first.  Results never depend on it.  All NULL/0 = off (one block per 64-beam tile instead).
        I = N*A*march_ipa items, march_ipa = ceil(num_beams/32) <= 256. */
-    uint32_t *march_cost;           /* [I]     initialised to 0xFFFFFFFF (= unknown) by the caller */
+    uint32_t *march_cost;           /* [N*A*256] indexed by (agent << 8 | item); initialised to 0xFFFFFFFF (= unknown) */
     uint32_t *march_order;          /* [3][I]  */
     uint32_t *march_count;          /* [4]     zero-initialised by the caller */
     int32_t march_ipa;

@@ -44,7 +44,7 @@ class F110Sim(C.Structure):
                 ('collisions', _dp), ('collision_idx', _dp),
                 ('current_time', _dp), ('lap_times', _dp), ('lap_counts', _dp), ('toggle_list', _dp),
                 ('near_starts', _dp), ('start_xs', _dp), ('start_ys', _dp), ('start_thetas', _dp),
-                ('start_rot', _dp), ('done', _dp), ('checkpoint_done', _dp),
+                ('start_rot', _dp), ('done', _dp), ('checkpoint_done', _dp), ('env_arrivals', _dp),
                 ('lookup_counter', _dp), ('tick_counter', _dp),
                 ('march_cost', _dp), ('march_order', _dp), ('march_count', _dp), ('march_ipa', C.c_int32),
                 ('noise_std', C.c_double), ('noise_seed', C.c_uint64)]
@@ -68,6 +68,8 @@ SIGNATURES = {
     'f110_env_reset': (C.c_int, [_P(F110Sim), _dp, _dp, _dp]),
     'f110_env_post_step': (C.c_int, [_P(F110Sim), _dp]),
     'f110_autoreset': (C.c_int, [_P(F110Sim), _dp, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _dp]),
+    'f110_tick': (C.c_int, [_P(F110Sim), _P(F110Map), _P(F110Beams), _dp, C.c_int32, _dp, C.c_int32, C.c_int32,
+                            C.c_uint64, _dp]),
     'f110_step_host': (C.c_int, [_P(F110Sim), _P(F110Map), _P(F110Beams), _dp, _dp, _P(F110HostObs), _dp]),
     'f110_scan': (C.c_int, [_P(F110Map), _P(F110Beams), _dp, C.c_int32, _dp, _dp, _dp, _dp]),
     'f110_vehicle_dynamics_st': (C.c_int, [_dp, _dp, _dp, C.c_int32, _dp, _dp]),

@@ -9,6 +9,19 @@
 namespace f110 {
 
 // collision_models.py:218-260 get_trmtx + get_vertices -> (rl, rr, fr, fl), v[2*i] = x, v[2*i+1] = y
+// (cos, sin of the yaw are passed in: k_dynamics computes them once per agent and tick)
+__device__ __forceinline__ void get_vertices_cs(double px, double py, double c, double s, double length, double width,
+                                                double v[8]) {
+    const double hl = length / 2, hw = width / 2;
+    const double lx[4] = { -hl, -hl, hl, hl };
+    const double ly[4] = { hw, -hw, -hw, hw };
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[2 * i] = (c * lx[i] + (-s) * ly[i]) + px;
+        v[2 * i + 1] = (s * lx[i] + c * ly[i]) + py;
+    }
+}
+
 __device__ __forceinline__ void get_vertices(double px, double py, double th, double length, double width,
                                              double v[8]) {
     double c = cos(th), s = sin(th);

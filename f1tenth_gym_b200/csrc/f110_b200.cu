@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
     }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= NA) return;
+    // the tick counter advances once per tick, here, before any kernel of the tick reads it (noise stream id,
+    // auto-reset draw); nothing else in this kernel uses it
+    if (a == 0 && s.tick_counter) *s.tick_counter += 1ull;
     const double *p = s.params + (size_t)(a % s.num_agents) * F110_NPARAM;
     double st[7];
 #pragma unroll
@@ -139,9 +142,11 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
     double2 *sp = reinterpret_cast<double2 *>(s.scan_pose) + 2 * (size_t)a;
     sp[0] = make_double2(sx, sy);
     sp[1] = make_double2(st[4], theta_index0(st[4], fov, theta_dis_f));
-    s.agent_poses[3 * (size_t)a] = st[0];
-    s.agent_poses[3 * (size_t)a + 1] = st[1];
-    s.agent_poses[3 * (size_t)a + 2] = st[4];
+    // pose snapshot (Simulator.agent_poses, base_classes.py:574) + cos/sin of the yaw: every vertex / heading
+    // computation of the finalize kernel reuses them instead of re-evaluating fp64 trig per opponent
+    double *ap = s.agent_poses + 5 * (size_t)a;
+    ap[0] = st[0]; ap[1] = st[1]; ap[2] = st[4];
+    ap[3] = cos(st[4]); ap[4] = sin(st[4]);
     s.wall_flag[a] = 0;
 }
 
@@ -205,33 +210,36 @@ __global__ void __launch_bounds__(256) k_raymarch(MapView m, BeamView bv, MarchA
     }
 }
 
-// ------------------------------------------------------------------------------------ k_finalize
-// Warp per agent (base_classes.py:536-550 check_collision, :579-589 update_scan loop).
-__global__ void __launch_bounds__(128) k_finalize(f110_sim s, BeamView bv) {
+// ------------------------------------------------------------------------------------ finalize
+// One warp finalises one agent (base_classes.py:536-550 check_collision, :579-589 update_scan loop).
+__device__ __forceinline__ void finalize_agent(const f110_sim &s, const BeamView &bv, int a, int lane,
+                                               double max_scan_range) {
     const int NA = s.num_envs * s.num_agents;
-    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (a >= NA) return;
     const int A = s.num_agents;
     const int env = a / A, slot = a - env * A;
     const int hit = s.wall_flag[a];
-    const double px = s.state[a], py = s.state[(size_t)NA + a];
+    const double *pa = s.agent_poses + 5 * (size_t)a;
+    const double px = pa[0], py = pa[1];      // == state[0], state[1]
     // check_ttc zeroes state[3:] — including the yaw — before the opponent ray-cast reads it (:246-249, :225)
-    const double yaw = hit ? 0.0 : s.state[(size_t)4 * NA + a];
-    __syncwarp();
+    const double yaw = hit ? 0.0 : pa[2];
+    const double cyaw = hit ? 1.0 : pa[3], syaw = hit ? 0.0 : pa[4];
     if (hit && lane < 4) s.state[(size_t)(3 + lane) * NA + a] = 0.0;
 
     // GJK against the other agents of this env, lower index first (collision_multiple :184-212)
     int col = 0, cidx = -1;
     if (A > 1) {
         double vme[8];
-        const double *pa = s.agent_poses + 3 * (size_t)a;
-        get_vertices(pa[0], pa[1], pa[2], s.sim_length, s.sim_width, vme);
+        get_vertices_cs(pa[0], pa[1], pa[3], pa[4], s.sim_length, s.sim_width, vme);
+        // two car bodies can only overlap if their centres are closer than one body diagonal; beyond that
+        // (with a 0.1 % margin) the shapes are strictly separated and GJK returns False, so it is not run
+        const double reach2 = (s.sim_length * s.sim_length + s.sim_width * s.sim_width) * 1.001;
         for (int j = lane; j < A; j += 32) {
             if (j == slot) continue;
-            const double *pb = s.agent_poses + 3 * (size_t)(env * A + j);
+            const double *pb = s.agent_poses + 5 * (size_t)(env * A + j);
+            const double ddx = pb[0] - pa[0], ddy = pb[1] - pa[1];
+            if (ddx * ddx + ddy * ddy > reach2) continue;
             double vo[8];
-            get_vertices(pb[0], pb[1], pb[2], s.sim_length, s.sim_width, vo);
+            get_vertices_cs(pb[0], pb[1], pb[3], pb[4], s.sim_length, s.sim_width, vo);
             bool c = (slot < j) ? gjk_collision(vme, vo) : gjk_collision(vo, vme);
             if (c) { col = 1; cidx = max(cidx, j); }
         }
@@ -251,15 +259,42 @@ __global__ void __launch_bounds__(128) k_finalize(f110_sim s, BeamView bv) {
         const double *p = s.params + (size_t)slot * F110_NPARAM;
         const double length = p[P_LENGTH], width = p[P_WIDTH];
         float *scan = s.scans + (size_t)a * bv.num_beams;
+        // an opponent whose nearest point is farther than any range the scan can hold (max_range plus noise
+        // head-room) cannot shorten a beam: ray_cast would leave the scan unchanged, so it is skipped
+        const double half_diag = 0.5 * sqrt(length * length + width * width);
         for (int j = 0; j < A; j++) {
             if (j == slot) continue;
-            const double *pb = s.agent_poses + 3 * (size_t)(env * A + j);
+            const double *pb = s.agent_poses + 5 * (size_t)(env * A + j);
+            {
+                const double ddx = pb[0] - px, ddy = pb[1] - py;
+                const double far = max_scan_range + half_diag;
+                if (ddx * ddx + ddy * ddy > far * far) continue;
+            }
             double v[8];
-            get_vertices(pb[0], pb[1], pb[2], length, width, v);
+            get_vertices_cs(pb[0], pb[1], pb[3], pb[4], length, width, v);
             int lo, hi;
-            blocked_view_indices(px, py, yaw, v, bv.scan_angles, bv.num_beams, bv.fov, bv.angle_increment, lo, hi);
+            double phi;
+            blocked_view_indices_warp(px, py, cyaw, syaw, v, bv.scan_angles, bv.num_beams, bv.fov, bv.angle_increment,
+                                      lane, pb[0], pb[1], lo, hi, phi);
+            // When the opponent straddles the rear cut of the field of view the window is ALL beams
+            // (laser_models.py:310-315 takes min/max of the four nearest-beam indices).  A ray can only meet an
+            // edge if it points into the cone that contains the opponent's bounding circle, so beams outside
+            // that cone (+0.05 rad of slack) would get four `inf` ranges and leave the scan unchanged: skip them.
+            double cone = 4.0;      // > pi: no filtering when the ego is inside / next to the bounding circle
+            {
+                const double ddx = pb[0] - px, ddy = pb[1] - py;
+                const double dist = sqrt(ddx * ddx + ddy * ddy);
+                if (dist > 1.25 * half_diag) cone = asin(half_diag / dist) + 0.05;
+            }
             for (int i = lo + lane; i <= hi; i += 32) {
+                const float cur = scan[i];          // issued early: often an L2/DRAM miss (the march just wrote it)
                 double bt = yaw + bv.scan_angles[i];
+                double dl = bt - phi;
+                dl = dl - (2 * M_PI) * rint(dl * (1.0 / (2 * M_PI)));
+                // (the mirrored cone is kept too: get_range's collinear branch, laser_models.py:275-278, has no
+                // direction test, so a beam pointing exactly away along an edge line still reports that edge)
+                const double adl = fabs(dl);
+                if (adl > cone && (M_PI - adl) > cone) continue;
                 double v3x = cos(bt + M_PI / 2.), v3y = sin(bt + M_PI / 2.);
                 double r = INFINITY;
 #pragma unroll
@@ -269,17 +304,25 @@ __global__ void __launch_bounds__(128) k_finalize(f110_sim s, BeamView bv) {
                     if (d < r) r = d;
                 }
                 float rf = (float)r;
-                if (rf < scan[i]) scan[i] = rf;
+                if (rf < cur) scan[i] = rf;
             }
             __syncwarp();
         }
     }
-    // tick counter: bumped once per f110_step by the last kernel of the tick; the march-hint list counters
-    // are consumed by now (k_march ran) and are refilled by the next tick's k_dynamics
-    if (a == 0 && lane == 0) {
-        if (s.tick_counter) *s.tick_counter += 1ull;
-        if (s.march_count) { s.march_count[0] = 0u; s.march_count[1] = 0u; s.march_count[2] = 0u; }
-    }
+}
+
+// the march work-queue counters are consumed once k_march has run; the next tick's k_dynamics refills them
+__device__ __forceinline__ void end_of_tick_housekeeping(const f110_sim &s) {
+    if (s.march_count) { s.march_count[0] = 0u; s.march_count[1] = 0u; s.march_count[2] = 0u; }
+}
+
+// f110_step: warp per agent
+__global__ void __launch_bounds__(128, 8) k_finalize(f110_sim s, BeamView bv, double max_scan_range) {
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= s.num_envs * s.num_agents) return;
+    finalize_agent(s, bv, a, lane, max_scan_range);
+    if (a == 0 && lane == 0) end_of_tick_housekeeping(s);
 }
 
 // ------------------------------------------------------------------------------------ reset kernels
@@ -332,10 +375,8 @@ __global__ void k_env_reset(f110_sim s, const double *__restrict__ poses, const 
     env_counters_reset(s, env, poses + 3 * (size_t)env * s.num_agents);
 }
 
-// f110_env.py:294-302 + _check_done :204-246, thread per env
-__global__ void k_env_post_step(f110_sim s) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= s.num_envs) return;
+// f110_env.py:294-302 + _check_done :204-246, one thread per env
+__device__ __forceinline__ void env_post_step_one(const f110_sim &s, int env) {
     const int A = s.num_agents, NA = s.num_envs * s.num_agents;
     const double left_t = 2, right_t = 2;
     const double now = s.current_time[env] + s.timestep;
@@ -368,19 +409,31 @@ __global__ void k_env_post_step(f110_sim s) {
     s.done[env] = ((s.collisions[(size_t)env * A + s.ego_idx] != 0.0) || all_done) ? 1 : 0;
 }
 
+__global__ void k_env_post_step(f110_sim s) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < s.num_envs) env_post_step_one(s, env);
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
 
-__global__ void k_autoreset(f110_sim s, const double *__restrict__ start_poses, int num_start, int pose_gap,
-                            uint64_t seed, const unsigned long long *tick_counter, uint64_t tick_host) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= s.num_envs) return;
+struct AutoResetArgs {
+    const double *start_poses;   // [num_start][3] or NULL = off
+    int num_start, pose_gap;
+    uint64_t seed, tick_host;
+};
+
+// one thread per env: reset the env if its ego collided (benchmark / RL convenience)
+__device__ __forceinline__ void autoreset_one(const f110_sim &s, int env, const AutoResetArgs &ar) {
     const int A = s.num_agents, NA = s.num_envs * s.num_agents;
     if (s.collisions[(size_t)env * A + s.ego_idx] == 0.0) return;
-    const uint64_t tick = tick_counter ? (uint64_t)*tick_counter : tick_host;
+    const double *__restrict__ start_poses = ar.start_poses;
+    const int num_start = ar.num_start, pose_gap = ar.pose_gap;
+    const uint64_t seed = ar.seed;
+    const uint64_t tick = s.tick_counter ? (uint64_t)*s.tick_counter : ar.tick_host;
     uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (tick + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(env + 1));
     int k = (int)((double)(h >> 11) * (1.0 / 9007199254740992.0) * num_start);
     if (k >= num_start) k = num_start - 1;
@@ -402,6 +455,36 @@ __global__ void k_autoreset(f110_sim s, const double *__restrict__ start_poses, 
         mark_march_cost_unknown(s, a);
     }
     if (s.current_time && A <= 32) env_counters_reset(s, env, pose3);
+}
+
+__global__ void k_autoreset(f110_sim s, AutoResetArgs ar) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < s.num_envs) autoreset_one(s, env, ar);
+}
+
+// f110_tick: warp per agent; the warp that finishes an env last (per-env arrival counter) also runs the F110Env
+// lap logic and the auto-reset for that env: k_finalize + k_env_post_step + k_autoreset in one launch
+__global__ void __launch_bounds__(128, 8) k_tail(f110_sim s, BeamView bv, int env_level, AutoResetArgs ar,
+                                                 double max_scan_range) {
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= s.num_envs * s.num_agents) return;
+    finalize_agent(s, bv, a, lane, max_scan_range);
+    __syncwarp();
+    if (lane == 0) {
+        const int env = a / s.num_agents;
+        bool last = true;
+        if (s.num_agents > 1) {
+            __threadfence();                                     // publish this agent's state / collisions
+            last = atomicAdd(s.env_arrivals + env, 1) == s.num_agents - 1;
+            if (last) { s.env_arrivals[env] = 0; __threadfence(); }
+        }
+        if (last) {
+            if (env_level) env_post_step_one(s, env);
+            if (ar.start_poses) autoreset_one(s, env, ar);
+        }
+        if (a == 0) end_of_tick_housekeeping(s);
+    }
 }
 
 // ------------------------------------------------------------------------------------ standalone kernels
@@ -563,6 +646,23 @@ static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArg
     return F110_OK;
 }
 
+template <int PT>
+static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned blocks, bool coded, bool noise, bool count,
+                              cudaStream_t st) {
+    if (k.trace) {
+        if (coded) k_march_persistent<true, false, false, true, PT><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<false, false, false, true, PT><<<blocks, PT, 0, st>>>(k, mq);
+    } else if (coded) {
+        if (count) k_march_persistent<true, false, true, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+        else if (noise) k_march_persistent<true, true, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<true, false, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+    } else {
+        if (count) k_march_persistent<false, false, true, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+        else if (noise) k_march_persistent<false, true, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<false, false, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+    }
+}
+
 template <int MINB>
 static void launch_march(const MarchK &k, dim3 grid, bool coded, bool noise, bool count, cudaStream_t st) {
     if (coded) {
@@ -604,8 +704,14 @@ const char *f110_status_string(int status) {
 
 const char *f110_last_cuda_error(void) { return g_cuda_err; }
 
+struct TailOpts {
+    bool fused;              // k_tail instead of k_finalize
+    int env_level;
+    AutoResetArgs ar;
+};
+
 static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions,
-                     cudaStream_t st, cudaEvent_t *ev /* NULL or [4] */) {
+                     cudaStream_t st, cudaEvent_t *ev /* NULL or [4] */, const TailOpts *tail = nullptr) {
     int rc;
     if ((rc = check_sim(sim)) || (rc = check_map(map)) || (rc = check_beams(beams))) return rc;
     if (!actions) return F110_ERR_INVALID;
@@ -657,18 +763,9 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
             const unsigned blocks = (unsigned)num_sms() * 4u;
-            if (k.trace) {
-                if (coded) k_march_persistent<true, false, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else k_march_persistent<false, false, false, true><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-            } else if (coded) {
-                if (count) k_march_persistent<true, false, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else if (noise) k_march_persistent<true, true, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else k_march_persistent<true, false, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-            } else {
-                if (count) k_march_persistent<false, false, true, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else if (noise) k_march_persistent<false, true, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-                else k_march_persistent<false, false, false, false><<<blocks, F110_MARCH_PT, 0, st>>>(k, mq);
-            }
+            if (variant == 11) launch_persistent<448>(k, mq, blocks, coded, noise, count, st);
+            else if (variant == 12) launch_persistent<384>(k, mq, blocks, coded, noise, count, st);
+            else launch_persistent<512>(k, mq, blocks, coded, noise, count, st);
         } else {
             const dim3 grid((unsigned)NA, (unsigned)bpa);
             if (variant == 9) launch_march<24>(k, grid, coded, noise, count, st);
@@ -696,8 +793,19 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
 marched:
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 
-    k_finalize<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv);
-    LAUNCH_CHECK("k_finalize");
+    // largest value a scan entry can hold: the max_range clamp plus 8 sigma of the optional noise
+    const double max_scan = map->max_range + 8.0 * (sim->noise_std > 0.0 ? sim->noise_std : 0.0) + 1e-3;
+    if (tail && tail->fused && (sim->num_agents == 1 || sim->env_arrivals)) {
+        k_tail<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv, tail->env_level, tail->ar, max_scan);
+        LAUNCH_CHECK("k_tail");
+    } else {
+        k_finalize<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv, max_scan);
+        LAUNCH_CHECK("k_finalize");
+        if (tail && tail->fused) {     // no arrival counters bound: same semantics with separate launches
+            if (tail->env_level) { k_env_post_step<<<(sim->num_envs + 127) / 128, 128, 0, st>>>(*sim); LAUNCH_CHECK("k_env_post_step"); }
+            if (tail->ar.start_poses) { k_autoreset<<<(sim->num_envs + 127) / 128, 128, 0, st>>>(*sim, tail->ar); LAUNCH_CHECK("k_autoreset"); }
+        }
+    }
     if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
     return F110_OK;
 }
@@ -766,10 +874,24 @@ int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_s
     if ((rc = check_sim(sim))) return rc;
     if (!start_poses || num_start <= 0) return F110_ERR_INVALID;
     if (sim->ego_idx < 0 || sim->ego_idx >= sim->num_agents) return F110_ERR_AGENT_INDEX;
-    k_autoreset<<<(sim->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sim, start_poses, num_start, pose_gap,
-                                                                               seed, sim->tick_counter, tick);
+    AutoResetArgs ar;
+    ar.start_poses = start_poses; ar.num_start = num_start; ar.pose_gap = pose_gap; ar.seed = seed; ar.tick_host = tick;
+    k_autoreset<<<(sim->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sim, ar);
     LAUNCH_CHECK("k_autoreset");
     return F110_OK;
+}
+
+int f110_tick(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions,
+              int32_t env_level, const double *start_poses, int32_t num_start, int32_t pose_gap, uint64_t seed,
+              void *stream) {
+    int rc;
+    if ((rc = check_sim(sim))) return rc;
+    if (env_level && (rc = check_env_arrays(sim))) return rc;
+    if (start_poses && (num_start <= 0 || sim->ego_idx < 0 || sim->ego_idx >= sim->num_agents)) return F110_ERR_INVALID;
+    TailOpts t;
+    t.fused = true; t.env_level = env_level;
+    t.ar.start_poses = start_poses; t.ar.num_start = num_start; t.ar.pose_gap = pose_gap; t.ar.seed = seed; t.ar.tick_host = 0;
+    return step_impl(sim, map, beams, actions, (cudaStream_t)stream, nullptr, &t);
 }
 
 int f110_step_host(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions_host,
@@ -780,9 +902,12 @@ int f110_step_host(const f110_sim *sim, const f110_map *map, const f110_beams *b
     cudaStream_t st = (cudaStream_t)stream;
     const size_t NA = (size_t)sim->num_envs * sim->num_agents;
     CUDA_TRY(cudaMemcpyAsync(actions_dev_scratch, actions_host, NA * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    if ((rc = f110_step(sim, map, beams, actions_dev_scratch, stream))) return rc;
     const bool env_level = sim->current_time && sim->done;
-    if (env_level && (rc = f110_env_post_step(sim, stream))) return rc;
+    if (env_level && (rc = check_env_arrays(sim))) return rc;
+    TailOpts t;
+    t.fused = true; t.env_level = env_level ? 1 : 0;
+    t.ar.start_poses = nullptr; t.ar.num_start = 0; t.ar.pose_gap = 0; t.ar.seed = 0; t.ar.tick_host = 0;
+    if ((rc = step_impl(sim, map, beams, actions_dev_scratch, st, nullptr, &t))) return rc;
     if (out->scans)
         CUDA_TRY(cudaMemcpyAsync(out->scans, sim->scans, NA * beams->num_beams * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out->state)

@@ -204,6 +204,40 @@ __device__ __forceinline__ int nearest_beam(const double *__restrict__ scan_angl
     return best;
 }
 
+// laser_models.py:282-315 get_blocked_view_indices, warp-cooperative: lanes 0-3 take one vertex each and lane 4
+// the ego heading, so the five atan2 evaluations run as ONE pass through the atan2 code instead of five.
+// (cos_yaw, sin_yaw) = (cos, sin)(pose yaw).  All 32 lanes must call; every lane gets the result.
+__device__ __forceinline__ void blocked_view_indices_warp(double px, double py, double cos_yaw, double sin_yaw,
+                                                          const double v[8], const double *__restrict__ scan_angles,
+                                                          int num_beams, double fov, double angle_increment, int lane,
+                                                          double cx, double cy, int &min_ind, int &max_ind,
+                                                          double &centre_dir) {
+    double ay, ax;
+    const int k = lane & 3;
+    if (lane == 4) { ay = sin_yaw; ax = cos_yaw; }
+    else if (lane == 5) { ay = cy - py; ax = cx - px; }      // world direction to the opponent's centre
+    else {
+        // (select with compile-time indices: a dynamically indexed v[] would live in local memory)
+        const double vkx = (k == 0) ? v[0] : (k == 1) ? v[2] : (k == 2) ? v[4] : v[6];
+        const double vky = (k == 0) ? v[1] : (k == 1) ? v[3] : (k == 2) ? v[5] : v[7];
+        const double vx = vkx - px, vy = vky - py;
+        const double norm = sqrt(vx * vx + vy * vy);
+        ax = vx / norm; ay = vy / norm;
+    }
+    const double at = atan2(ay, ax);
+    const double ego_a = __shfl_sync(0xffffffffu, at, 4);
+    centre_dir = __shfl_sync(0xffffffffu, at, 5);
+    double angle = ego_a - at;
+    if (angle > M_PI) angle = angle - 2 * M_PI;
+    else if (angle < -M_PI) angle = angle + 2 * M_PI;
+    int ind = nearest_beam(scan_angles, num_beams, fov, angle_increment, -angle);
+    int lo = ind, hi = ind;       // lanes 0-3 hold the four vertex indices (lanes >= 6 mirror lane & 3)
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, 1)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, 2)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
+    min_ind = __shfl_sync(0xffffffffu, lo, 0);
+    max_ind = __shfl_sync(0xffffffffu, hi, 0);
+}
+
 // laser_models.py:282-315 get_blocked_view_indices
 __device__ __forceinline__ void blocked_view_indices(double px, double py, double yaw, const double v[8],
                                                      const double *__restrict__ scan_angles, int num_beams,

@@ -178,9 +178,8 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
 
 // persistent: gridDim.x blocks of 512 threads stay resident; queue position q = k * gridDim.x + blockIdx.x.
 // cost[] is indexed by the packed item id (agent << 8 | slice), so no multiply/divide is needed per item.
-#define F110_MARCH_PT 512
-template <bool CODED, bool NOISE, bool COUNT, bool TRACE>
-__global__ void __launch_bounds__(F110_MARCH_PT, 4) k_march_persistent(const MarchK p, const MarchQueue mq) {
+template <bool CODED, bool NOISE, bool COUNT, bool TRACE, int PT>
+__global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
     if (threadIdx.x == 0) s_next = 0u;
     __syncthreads();

@@ -126,7 +126,7 @@ class Simulator(object):
         self.steer_buf = torch.zeros((2, NA), **f64)
         self.steer_cnt = torch.zeros((NA,), **i32)
         self.scan_pose = torch.zeros((NA, 4), **f64)
-        self.agent_poses = torch.zeros((NA, 3), **f64)
+        self.agent_poses = torch.zeros((NA, 5), **f64)
         self.scans = torch.zeros((NA, B), dtype=torch.float32, device=dev)
         self.wall_flag = torch.zeros((NA,), **i32)
         self.collisions = torch.zeros((NA,), **f64)
@@ -143,6 +143,7 @@ class Simulator(object):
         self.start_rot = torch.eye(2, **f64).reshape(1, 4).repeat(N, 1).contiguous()
         self.done = torch.zeros((N,), dtype=torch.uint8, device=dev)
         self.checkpoint_done = torch.zeros((NA,), dtype=torch.uint8, device=dev)
+        self.env_arrivals = torch.zeros((N,), **i32)
         self.lookup_counter = torch.zeros((1,), dtype=torch.int64, device=dev) if count_lookups else None
         self.tick_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
         # work queue of the persistent ray-march kernel (csrc/march.cuh): last tick's heavy items go first
@@ -163,7 +164,7 @@ class Simulator(object):
             nat.ptr(self.lap_times), nat.ptr(self.lap_counts), nat.ptr(self.toggle_list),
             nat.ptr(self.near_starts), nat.ptr(self.start_xs), nat.ptr(self.start_ys),
             nat.ptr(self.start_thetas), nat.ptr(self.start_rot), nat.ptr(self.done),
-            nat.ptr(self.checkpoint_done), nat.ptr(self.lookup_counter), nat.ptr(self.tick_counter),
+            nat.ptr(self.checkpoint_done), nat.ptr(self.env_arrivals), nat.ptr(self.lookup_counter), nat.ptr(self.tick_counter),
             nat.ptr(self.march_cost), nat.ptr(self.march_order), nat.ptr(self.march_count), self.march_ipa,
             float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
         self._graph = None
@@ -261,6 +262,16 @@ class Simulator(object):
         nat.check(nat.lib().f110_autoreset(C.byref(self.c), nat.ptr(start_poses), start_poses.shape[0],
                                            pose_gap, int(seed), 0, _stream_ptr(self.device)))
 
+    def tick(self, control_inputs, env_level=True, autoreset_poses=None, pose_gap=23, seed=12345):
+        """One whole tick in three launches (C ABI f110_tick): step + lap logic + optional auto-reset, same
+        results as step(); env_post_step(); autoreset()."""
+        a = self._actions_tensor(control_inputs)
+        n = 0 if autoreset_poses is None else autoreset_poses.shape[0]
+        nat.check(nat.lib().f110_tick(C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c), nat.ptr(a),
+                                      1 if env_level else 0, nat.ptr(autoreset_poses), n, pose_gap, int(seed),
+                                      _stream_ptr(self.device)))
+        return self.observations()
+
     def observations(self):
         N, A, B = self.num_envs, self.num_agents, self.num_beams
         st = self.state
@@ -280,13 +291,10 @@ class Simulator(object):
         L = nat.lib()
 
         def tick():
-            nat.check(L.f110_step(C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c),
-                                  nat.ptr(actions), _stream_ptr(self.device)))
-            if env_level:
-                nat.check(L.f110_env_post_step(C.byref(self.c), _stream_ptr(self.device)))
-            if autoreset_poses is not None:
-                nat.check(L.f110_autoreset(C.byref(self.c), nat.ptr(autoreset_poses), autoreset_poses.shape[0],
-                                           pose_gap, int(autoreset_seed), 0, _stream_ptr(self.device)))
+            n = 0 if autoreset_poses is None else autoreset_poses.shape[0]
+            nat.check(L.f110_tick(C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c), nat.ptr(actions),
+                                  1 if env_level else 0, nat.ptr(autoreset_poses), n, pose_gap, int(autoreset_seed),
+                                  _stream_ptr(self.device)))
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):

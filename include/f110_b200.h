@@ -79,7 +79,7 @@ typedef struct {
     double *steer_buf;              /* [2][N*A]   steering delay FIFO, row 0 = newest (base_classes.py:270-278) */
     int32_t *steer_cnt;             /* [N*A] */
     double *scan_pose;              /* [N*A][4]   (scan_x, scan_y, yaw, theta_index0) written by the dynamics kernel */
-    double *agent_poses;            /* [N*A][3]   Simulator.agent_poses snapshot (base_classes.py:574) */
+    double *agent_poses;            /* [N*A][5]   Simulator.agent_poses snapshot (base_classes.py:574): x, y, yaw, cos yaw, sin yaw */
     float *scans;                   /* [N*A][num_beams] */
     int32_t *wall_flag;             /* [N*A]      RaceCar.in_collision (iTTC) */
     double *collisions;             /* [N*A]      obs['collisions'] (0./1.) */
@@ -92,6 +92,7 @@ typedef struct {
     double *start_rot;              /* [N][4] */
     uint8_t *done;                  /* [N] */
     uint8_t *checkpoint_done;       /* [N*A]  info['checkpoint_done'] */
+    int32_t *env_arrivals;          /* [N] zero-initialised scratch of f110_tick (per-env arrival counter), or NULL */
     unsigned long long *lookup_counter;   /* optional [1]: total DT lookups (roofline denominator); NULL = off */
     unsigned long long *tick_counter;     /* optional [1]: incremented by every f110_step; keys the noise stream
                                              and the auto-reset draw so that CUDA-graph replays stay distinct */
@@ -140,6 +141,13 @@ int f110_env_post_step(const f110_sim *sim, void *stream);
  * counter-based hash of (seed, tick, env); agent i takes start_poses[(k - pose_gap*i) mod K]. */
 int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_start, int32_t pose_gap,
                    uint64_t seed, uint64_t tick, void *stream);
+
+/* One whole tick in three launches: f110_step + (env_level != 0) f110_env_post_step + (start_poses != NULL)
+ * f110_autoreset, with the last three fused into one kernel (one warp per env).  Same results as calling
+ * the three entry points in that order.  This is what a training loop / CUDA graph should replay. */
+int f110_tick(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions,
+              int32_t env_level, const double *start_poses, int32_t num_start, int32_t pose_gap, uint64_t seed,
+              void *stream);
 
 /* Same tick through HOST buffers: copies actions H2D, runs f110_step (+ f110_env_post_step when the
  * lap arrays are bound), copies the observation D2H and synchronises the stream.

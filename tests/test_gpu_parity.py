@@ -360,6 +360,30 @@ def test_autoreset(f110, dev, example_map):
     assert (obs['collisions'][:, 0] != 0).float().mean().item() < 0.2
 
 
+def test_fused_tick_equals_separate_calls(f110, dev, example_map):
+    """f110_tick (finalize + lap logic + auto-reset in one kernel) == f110_step; f110_env_post_step; f110_autoreset."""
+    N, A, T = 192, 2, 260
+    rng = np.random.default_rng(9)
+    poses = _start_poses(f110, rng, N, A, gap=4)
+    start = torch.from_numpy(f110.maps.load_waypoints()).to(dev)
+    sep = make_sim(f110, dev, example_map, N, A)
+    fus = make_sim(f110, dev, example_map, N, A, march_queue=False)     # also: with and without the work queue
+    sep.env_reset(poses)
+    fus.env_reset(poses)
+    resets = 0
+    for t in range(T):
+        act = np.stack([rng.uniform(-0.4189, 0.4189, (N, A)), rng.uniform(0, 8, (N, A))], axis=2)
+        sep.step(act)
+        sep.env_post_step()
+        resets += int((sep.collisions.view(N, A)[:, 0] != 0).sum().item())
+        sep.autoreset(start, pose_gap=23, seed=77)
+        fus.tick(act, env_level=True, autoreset_poses=start, pose_gap=23, seed=77)
+    assert resets > 50
+    for name in ('state', 'scans', 'collisions', 'collision_idx', 'steer_cnt', 'steer_buf', 'lap_times', 'lap_counts',
+                 'toggle_list', 'near_starts', 'current_time', 'done', 'start_xs', 'start_rot'):
+        assert torch.equal(getattr(sep, name), getattr(fus, name)), name
+
+
 def test_scan_noise_statistics(f110, dev, example_map):
     N, A = 64, 1
     clean = make_sim(f110, dev, example_map, N, A)

@@ -926,6 +926,46 @@ int f110_step_host(const f110_sim *sim, const f110_map *map, const f110_beams *b
     return F110_OK;
 }
 
+int f110_step_host_async(const f110_sim *sim, const f110_map *map, const f110_beams *beams,
+                         const double *actions_host, double *actions_dev_scratch, const f110_host_obs *stage,
+                         const f110_host_obs *out, void *compute_stream, void *copy_stream, void *ev_tick_done,
+                         void *ev_copy_done) {
+    int rc;
+    if ((rc = check_sim(sim))) return rc;
+    if (!actions_host || !actions_dev_scratch || !stage || !out || !ev_tick_done || !ev_copy_done) return F110_ERR_INVALID;
+    cudaStream_t cs = (cudaStream_t)compute_stream, ps = (cudaStream_t)copy_stream;
+    cudaEvent_t e_tick = (cudaEvent_t)ev_tick_done, e_copy = (cudaEvent_t)ev_copy_done;
+    const size_t NA = (size_t)sim->num_envs * sim->num_agents;
+    const bool env_level = sim->current_time && sim->done;
+    if (env_level && (rc = check_env_arrays(sim))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(actions_dev_scratch, actions_host, NA * 2 * sizeof(double), cudaMemcpyHostToDevice, cs));
+    TailOpts t;
+    t.fused = true; t.env_level = env_level ? 1 : 0;
+    t.ar.start_poses = nullptr; t.ar.num_start = 0; t.ar.pose_gap = 0; t.ar.seed = 0; t.ar.tick_host = 0;
+    if ((rc = step_impl(sim, map, beams, actions_dev_scratch, cs, nullptr, &t))) return rc;
+    // the staging buffers may still be draining to the host from their previous use
+    CUDA_TRY(cudaStreamWaitEvent(cs, e_copy, 0));
+    struct Part { void *dst_dev, *dst_host; const void *src; size_t bytes; };
+    const Part parts[6] = {
+        { stage->scans, out->scans, sim->scans, NA * beams->num_beams * sizeof(float) },
+        { stage->state, out->state, sim->state, NA * 7 * sizeof(double) },
+        { stage->collisions, out->collisions, sim->collisions, NA * sizeof(double) },
+        { stage->done, out->done, env_level ? sim->done : nullptr, (size_t)sim->num_envs },
+        { stage->lap_times, out->lap_times, env_level ? sim->lap_times : nullptr, NA * sizeof(double) },
+        { stage->lap_counts, out->lap_counts, env_level ? sim->lap_counts : nullptr, NA * sizeof(double) },
+    };
+    for (int i = 0; i < 6; i++)
+        if (parts[i].dst_dev && parts[i].dst_host && parts[i].src)
+            CUDA_TRY(cudaMemcpyAsync(parts[i].dst_dev, parts[i].src, parts[i].bytes, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(cudaEventRecord(e_tick, cs));
+    CUDA_TRY(cudaStreamWaitEvent(ps, e_tick, 0));
+    for (int i = 0; i < 6; i++)
+        if (parts[i].dst_dev && parts[i].dst_host && parts[i].src)
+            CUDA_TRY(cudaMemcpyAsync(parts[i].dst_host, parts[i].dst_dev, parts[i].bytes, cudaMemcpyDeviceToHost, ps));
+    CUDA_TRY(cudaEventRecord(e_copy, ps));
+    return F110_OK;
+}
+
 int f110_scan(const f110_map *map, const f110_beams *beams, const double *poses, int32_t M, float *out_f32,
               double *out_f64, unsigned long long *lookup_counter, void *stream) {
     int rc;

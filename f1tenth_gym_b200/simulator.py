@@ -334,6 +334,49 @@ class Simulator(object):
                                            C.byref(io['_struct']), _stream_ptr(self.device)))
         return io
 
+    def make_host_pipeline(self, depth=2, with_scans=True):
+        """`depth` independent sets of (pinned host obs, device staging, events, actions scratch) for
+        step_host_async(); one shared copy stream."""
+        N, A, B = self.num_envs, self.num_agents, self.num_beams
+        NA = N * A
+        dev = self.device
+        copy_stream = torch.cuda.Stream(dev)
+        sets = []
+        for _ in range(depth):
+            io = self.make_host_io(with_scans)
+            st = {'scans': torch.zeros((NA, B), dtype=torch.float32, device=dev) if with_scans else None,
+                  'state': torch.zeros((7, NA), dtype=torch.float64, device=dev),
+                  'collisions': torch.zeros((NA,), dtype=torch.float64, device=dev),
+                  'done': torch.zeros((N,), dtype=torch.uint8, device=dev),
+                  'lap_times': torch.zeros((NA,), dtype=torch.float64, device=dev),
+                  'lap_counts': torch.zeros((NA,), dtype=torch.float64, device=dev)}
+            io['_stage'] = st
+            io['_stage_struct'] = nat.F110HostObs(nat.ptr(st['scans']), nat.ptr(st['state']), nat.ptr(st['collisions']),
+                                                  nat.ptr(st['done']), nat.ptr(st['lap_times']), nat.ptr(st['lap_counts']))
+            io['_actions_dev'] = torch.zeros((NA, 2), dtype=torch.float64, device=dev)
+            io['_ev_tick'] = torch.cuda.Event()
+            io['_ev_copy'] = torch.cuda.Event()
+            io['_ev_tick'].record()
+            io['_ev_copy'].record()
+            io['_copy_stream'] = copy_stream
+            sets.append(io)
+        torch.cuda.synchronize(dev)
+        return sets
+
+    def step_host_async(self, io):
+        """Enqueue one tick whose observation lands in io's pinned host buffers (C ABI f110_step_host_async);
+        returns immediately.  Call wait_host(io) before reading them or before reusing io."""
+        nat.check(nat.lib().f110_step_host_async(
+            C.byref(self.c), C.byref(self._map_struct), C.byref(self.beams.c), nat.ptr(io['actions']),
+            nat.ptr(io['_actions_dev']), C.byref(io['_stage_struct']), C.byref(io['_struct']),
+            _stream_ptr(self.device), C.c_void_p(io['_copy_stream'].cuda_stream),
+            C.c_void_p(io['_ev_tick'].cuda_event), C.c_void_p(io['_ev_copy'].cuda_event)))
+        return io
+
+    @staticmethod
+    def wait_host(io):
+        io['_ev_copy'].synchronize()
+
     def step_profile(self, control_inputs):
         """One tick with CUDA events around each kernel -> (dynamics_ms, raymarch_ms, finalize_ms)."""
         a = self._actions_tensor(control_inputs)

@@ -163,6 +163,18 @@ int f110_step_host(const f110_sim *sim, const f110_map *map, const f110_beams *b
                    const double *actions_host, double *actions_dev_scratch, const f110_host_obs *out,
                    void *stream);
 
+/* Pipelined variant for host-side consumers: the tick runs on `compute_stream`, its observation is
+ * snapshotted into the DEVICE staging buffers `stage` (same layout as f110_host_obs), and the D2H copies
+ * into `out` run on `copy_stream`, so that the copy of tick t overlaps the compute of tick t+1.  No host
+ * synchronisation: the caller alternates between two (stage, out, event) sets and, before reusing a set or
+ * reading its host buffers, waits for `ev_copy_done` (cudaEventSynchronize).  `ev_tick_done` and
+ * `ev_copy_done` are cudaEvent_t created by the caller.  Before overwriting `stage` the compute stream
+ * waits for the previous copy out of it (the event's last record). */
+int f110_step_host_async(const f110_sim *sim, const f110_map *map, const f110_beams *beams,
+                         const double *actions_host, double *actions_dev_scratch, const f110_host_obs *stage,
+                         const f110_host_obs *out, void *compute_stream, void *copy_stream, void *ev_tick_done,
+                         void *ev_copy_done);
+
 /* ---- standalone kernels (unit-parity surface; device pointers) ------------------------------- */
 
 /* ScanSimulator2D.scan without noise / get_scan (laser_models.py:148-186, 429-454): M poses -> [M][B]. */

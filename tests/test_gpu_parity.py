@@ -333,6 +333,36 @@ def test_graph_and_host_paths_match_eager(f110, dev, example_map):
     assert int(eager.tick_counter.item()) == T == int(graph.tick_counter.item())
 
 
+def test_host_pipeline_matches_sync(f110, dev, example_map):
+    N, A, T = 48, 2, 12
+    rng = np.random.default_rng(31)
+    poses = _start_poses(f110, rng, N, A)
+    acts = torch.from_numpy(np.stack([rng.uniform(-0.4189, 0.4189, (T, N * A)), rng.uniform(0, 8, (T, N * A))], axis=2))
+    sync = make_sim(f110, dev, example_map, N, A)
+    pipe = make_sim(f110, dev, example_map, N, A)
+    sync.env_reset(poses)
+    pipe.env_reset(poses)
+    io = sync.make_host_io()
+    sets = pipe.make_host_pipeline(depth=2)
+    ref = []
+    for t in range(T):
+        io['actions'].copy_(acts[t])
+        sync.step_host(io)
+        ref.append({k: io[k].clone() for k in ('scans', 'state', 'collisions', 'done', 'lap_times', 'lap_counts')})
+    got = [None] * T
+    for t in range(T + 2):
+        s_ = sets[t % 2]
+        pipe.wait_host(s_)
+        if t >= 2:
+            got[t - 2] = {k: s_[k].clone() for k in ref[0]}
+        if t < T:
+            s_['actions'].copy_(acts[t])
+            pipe.step_host_async(s_)
+    for t in range(T):
+        for k in ref[t]:
+            assert torch.equal(ref[t][k], got[t][k]), (t, k)
+
+
 def test_autoreset(f110, dev, example_map):
     N, A = 256, 2
     rng = np.random.default_rng(4)

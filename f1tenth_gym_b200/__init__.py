@@ -9,5 +9,6 @@ from .simulator import Integrator, Simulator, DeviceMap, DeviceBeams   # noqa: F
 from .env import F110Env                                              # noqa: F401
 from . import kernels, maps                                           # noqa: F401
 from .kernels import ScanSimulator2D                                  # noqa: F401
+from .planner import PurePursuitPlanner                               # noqa: F401
 
-__all__ = ['F110Env', 'Simulator', 'Integrator', 'ScanSimulator2D', 'DeviceMap', 'DeviceBeams', 'kernels', 'maps']
+__all__ = ['F110Env', 'Simulator', 'Integrator', 'ScanSimulator2D', 'PurePursuitPlanner', 'DeviceMap', 'DeviceBeams', 'kernels', 'maps']

@@ -18,6 +18,7 @@
 #include "dynamics.cuh"
 #include "lidar.cuh"
 #include "march.cuh"
+#include "planner.cuh"
 
 namespace f110 {
 
@@ -1036,6 +1037,18 @@ int f110_ray_cast(const f110_beams *beams, const double *poses, const double *op
     k_ray_cast<<<((long long)M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_view(beams), poses, opp_vertices,
                                                                                   M, scans, window);
     LAUNCH_CHECK("k_ray_cast");
+    return F110_OK;
+}
+
+int f110_pure_pursuit(const double *wx, const double *wy, const double *wv, int32_t num_waypoints, const double *pose_x,
+                      const double *pose_y, const double *pose_theta, int32_t M, double lookahead_distance, double vgain,
+                      double wheelbase, double max_reacquire, double *actions_out, void *stream) {
+    if (!wx || !wy || !wv || num_waypoints < 2 || !pose_x || !pose_y || !pose_theta || M <= 0 || !actions_out)
+        return F110_ERR_INVALID;
+    k_pure_pursuit<<<((long long)M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        wx, wy, wv, num_waypoints, pose_x, pose_y, pose_theta, M, lookahead_distance, vgain, wheelbase, max_reacquire,
+        actions_out);
+    LAUNCH_CHECK("k_pure_pursuit");
     return F110_OK;
 }
 

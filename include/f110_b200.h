@@ -204,6 +204,13 @@ int f110_ray_cast(const f110_beams *beams, const double *poses, const double *op
  * Box-Muller; statistical, not bit, parity with numpy's PCG64 stream. */
 int f110_scan_noise(float *scans, int64_t count, double std_dev, uint64_t seed, uint64_t offset, void *stream);
 
+/* Batched pure-pursuit policy (reference examples/waypoint_follow.py:15-217, PurePursuitPlanner.plan):
+ * waypoint columns wx, wy, wv [num_waypoints] and poses pose_x/y/theta [M] (device) -> actions_out [M][2] =
+ * (steering angle, speed), the layout f110_step consumes.  max_reacquire is 20.0 in the reference (:154). */
+int f110_pure_pursuit(const double *wx, const double *wy, const double *wv, int32_t num_waypoints, const double *pose_x,
+                      const double *pose_y, const double *pose_theta, int32_t M, double lookahead_distance, double vgain,
+                      double wheelbase, double max_reacquire, double *actions_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

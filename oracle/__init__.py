@@ -88,6 +88,7 @@ def lib():
         L.orc_rollout.restype = C.c_int64
         L.orc_rollout.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _dp, C.c_int, C.c_int,
                                   C.c_uint64, C.c_int, C.POINTER(C.c_int64)]
+        L.orc_pure_pursuit.argtypes = [_dp, _dp, _dp, C.c_int] + [C.c_double] * 7 + [_dp]
         L.orc_num_cores.restype = C.c_int
         _LIB = L
     return _LIB
@@ -318,6 +319,15 @@ def rollout(sims, ticks, start_poses, pose_gap=23, seed=12345, num_threads=0):
     tot = lib().orc_rollout(arr, len(sims), ticks, _p(start_poses), start_poses.shape[0], pose_gap,
                             seed, num_threads, C.byref(n))
     return tot, n.value
+
+
+def pure_pursuit(wx, wy, wv, pose, lookahead_distance, vgain, wheelbase, max_reacquire=20.0):
+    """examples/waypoint_follow.py PurePursuitPlanner.plan -> (speed, steering_angle)."""
+    wx, wy, wv = _f64(wx), _f64(wy), _f64(wv)
+    out = np.empty(2)
+    lib().orc_pure_pursuit(_p(wx), _p(wy), _p(wv), wx.shape[0], float(pose[0]), float(pose[1]), float(pose[2]),
+                           lookahead_distance, vgain, wheelbase, max_reacquire, _p(out))
+    return out[0], out[1]
 
 
 def num_cores():

@@ -667,3 +667,89 @@ int64_t orc_rollout(orc_sim_t **sims, int num_envs, int ticks, const double *sta
 }
 
 int orc_num_cores(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
+
+/* ------------------------------------------------------------------ pure-pursuit planner
+ * examples/waypoint_follow.py (paths relative to /root/reference/examples/):
+ *   nearest_point_on_trajectory :15-47, first_point_on_trajectory_intersecting_circle :49-131,
+ *   get_actuation :133-144, PurePursuitPlanner._get_current_waypoint :183-202, .plan :204-217.
+ * wx, wy, wv: waypoint x, y, speed columns [n].  out[0] = speed, out[1] = steering angle. */
+void orc_pure_pursuit(const double *wx, const double *wy, const double *wv, int n, double pose_x, double pose_y,
+                      double pose_theta, double lookahead_distance, double vgain, double wheelbase,
+                      double max_reacquire, double *out) {
+    /* nearest_point_on_trajectory */
+    int best = 0;
+    double best_d = 0, best_t = 0;
+    for (int i = 0; i < n - 1; i++) {
+        double dx = wx[i + 1] - wx[i], dy = wy[i + 1] - wy[i];
+        double l2 = dx * dx + dy * dy;
+        double dot = (pose_x - wx[i]) * dx + (pose_y - wy[i]) * dy;
+        double t = dot / l2;
+        if (t < 0.0) t = 0.0;
+        if (t > 1.0) t = 1.0;
+        double px = wx[i] + t * dx, py = wy[i] + t * dy;
+        double ex = pose_x - px, ey = pose_y - py;
+        double d = sqrt(ex * ex + ey * ey);
+        if (i == 0 || d < best_d) { best_d = d; best = i; best_t = t; }
+    }
+    double lx, ly, lv;
+    int have = 0;
+    if (best_d < lookahead_distance) {
+        /* first_point_on_trajectory_intersecting_circle(position, L, wpts, i + t, wrap=True) */
+        double tt = (double)best + best_t;
+        int start_i = (int)tt;
+        double start_t = fmod(tt, 1.0);
+        int first_i = -1000000;
+        for (int i = start_i; i < n - 1 && first_i == -1000000; i++) {
+            double sx = wx[i], sy = wy[i];
+            double Vx = (wx[i + 1] + 1e-6) - sx, Vy = (wy[i + 1] + 1e-6) - sy;
+            double a = Vx * Vx + Vy * Vy;
+            double b = 2.0 * (Vx * (sx - pose_x) + Vy * (sy - pose_y));
+            double c = (sx * sx + sy * sy) + (pose_x * pose_x + pose_y * pose_y) - 2.0 * (sx * pose_x + sy * pose_y) -
+                       lookahead_distance * lookahead_distance;
+            double disc = b * b - 4 * a * c;
+            if (disc < 0) continue;
+            disc = sqrt(disc);
+            double t1 = (-b - disc) / (2.0 * a), t2 = (-b + disc) / (2.0 * a);
+            if (i == start_i) {
+                if (t1 >= 0.0 && t1 <= 1.0 && t1 >= start_t) first_i = i;
+                else if (t2 >= 0.0 && t2 <= 1.0 && t2 >= start_t) first_i = i;
+            } else if (t1 >= 0.0 && t1 <= 1.0) first_i = i;
+            else if (t2 >= 0.0 && t2 <= 1.0) first_i = i;
+        }
+        if (first_i == -1000000) {
+            for (int i = -1; i < start_i && first_i == -1000000; i++) {
+                int i0 = ((i % n) + n) % n, i1 = (((i + 1) % n) + n) % n;
+                double sx = wx[i0], sy = wy[i0];
+                double Vx = (wx[i1] + 1e-6) - sx, Vy = (wy[i1] + 1e-6) - sy;
+                double a = Vx * Vx + Vy * Vy;
+                double b = 2.0 * (Vx * (sx - pose_x) + Vy * (sy - pose_y));
+                double c = (sx * sx + sy * sy) + (pose_x * pose_x + pose_y * pose_y) - 2.0 * (sx * pose_x + sy * pose_y) -
+                           lookahead_distance * lookahead_distance;
+                double disc = b * b - 4 * a * c;
+                if (disc < 0) continue;
+                disc = sqrt(disc);
+                double t1 = (-b - disc) / (2.0 * a), t2 = (-b + disc) / (2.0 * a);
+                if (t1 >= 0.0 && t1 <= 1.0) first_i = i;
+                else if (t2 >= 0.0 && t2 <= 1.0) first_i = i;
+            }
+        }
+        if (first_i != -1000000) {
+            /* current_waypoint[0:2] = wpts[i2, :] (python negative index -1 -> last row); speed from row i */
+            int i2 = first_i < 0 ? first_i + n : first_i;
+            lx = wx[i2]; ly = wy[i2]; lv = wv[best]; have = 1;
+        }
+    } else if (best_d < max_reacquire) {
+        lx = wx[best]; ly = wy[best]; lv = wv[best]; have = 1;
+    }
+    if (!have) { out[0] = 4.0; out[1] = 0.0; return; }
+    /* get_actuation */
+    double waypoint_y = sin(-pose_theta) * (lx - pose_x) + cos(-pose_theta) * (ly - pose_y);
+    double speed = lv, steer;
+    if (fabs(waypoint_y) < 1e-6) steer = 0.;
+    else {
+        double radius = 1 / (2.0 * waypoint_y / (lookahead_distance * lookahead_distance));
+        steer = atan(wheelbase / radius);
+    }
+    out[0] = vgain * speed;
+    out[1] = steer;
+}

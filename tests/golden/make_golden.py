@@ -284,7 +284,42 @@ def env_laps():
     print('env_laps ticks', len(rec['done']), 'final lap_times', rec['lap_times'][-1], 'lap_counts', rec['lap_counts'][-1])
 
 
+# ----------------------------------------------------------------------------- planner
+def kat_planner():
+    """PurePursuitPlanner.plan of examples/waypoint_follow.py at on-track, off-track (re-acquire) and far poses."""
+    import yaml
+    from argparse import Namespace
+    for name in ('gym', 'pyglet', 'pyglet.gl'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['pyglet.gl'].GL_POINTS = 0
+    sys.modules['pyglet'].gl = sys.modules['pyglet.gl']
+    ex = os.path.join(ref_import.REF_ROOT, 'examples')
+    if ex not in sys.path:
+        sys.path.insert(0, ex)
+    import waypoint_follow as wf
+    with open(os.path.join(ex, 'config_example_map.yaml')) as f:
+        conf = Namespace(**yaml.safe_load(f))
+    conf.wpt_path = os.path.join(ex, 'example_waypoints.csv')
+    wb = 0.17145 + 0.15875
+    pl = wf.PurePursuitPlanner(conf, wb)
+    W = pl.waypoints
+    rng = np.random.default_rng(77)
+    M = 2000
+    k = rng.integers(0, W.shape[0], M)
+    off = np.where(rng.random(M) < 0.7, rng.normal(0, 0.3, M), rng.uniform(-30, 30, M))
+    ang = rng.uniform(0, 2 * np.pi, M)
+    poses = np.stack([W[k, 1] + off * np.cos(ang), W[k, 2] + off * np.sin(ang), rng.uniform(-np.pi, 2 * np.pi, M)], axis=1)
+    poses[:40, :2] = W[k[:40], 1:3]                      # exactly on a waypoint
+    poses[40:60, :2] = W[-3:, 1:3].mean(axis=0)          # near the end of the list: wrap-around search
+    tlad, vgain = 0.82461887897713965, 1.375
+    out = np.array([pl.plan(p[0], p[1], p[2], tlad, vgain) for p in poses])     # (speed, steer)
+    out2 = np.array([pl.plan(p[0], p[1], p[2], 2.5, 0.9) for p in poses[:400]])
+    save('kat_planner.npz', poses=poses, speed_steer=out, speed_steer_l25=out2, tlad=tlad, vgain=vgain, wheelbase=wb)
+
+
 if __name__ == '__main__':
+    kat_planner()
     kat_reference_tests()
     kat_kernels()
     scans()

@@ -433,3 +433,32 @@ def test_scan_noise_statistics(f110, dev, example_map):
     noisy2 = make_sim(f110, dev, example_map, N, A, noise_std=0.01)
     noisy2.reset(poses)
     assert torch.equal(noisy2.step(z)['scans'].double(), b1)     # same seed -> same stream
+
+
+def test_planner_vs_reference_and_closed_loop(f110, dev, example_map):
+    k = g('kat_planner.npz')
+    pl = f110.PurePursuitPlanner(wb=float(k['wheelbase']), device=dev)
+    sp, st = pl.plan(k['poses'][:, 0], k['poses'][:, 1], k['poses'][:, 2], float(k['tlad']), float(k['vgain']))
+    assert np.abs(cpu(sp) - k['speed_steer'][:, 0]).max() < 1e-12
+    assert np.abs(cpu(st) - k['speed_steer'][:, 1]).max() < 1e-9
+    sp2, st2 = pl.plan(k['poses'][:400, 0], k['poses'][:400, 1], k['poses'][:400, 2], 2.5, 0.9)
+    assert np.abs(cpu(sp2) - k['speed_steer_l25'][:, 0]).max() < 1e-12
+    assert np.abs(cpu(st2) - k['speed_steer_l25'][:, 1]).max() < 1e-9
+    s1, a1 = pl.plan(0.7, 0.0, 1.37079632679, float(k['tlad']), float(k['vgain']))      # scalar, reference-shaped call
+    assert isinstance(s1, float) and isinstance(a1, float)
+    # closed loop entirely on the device: the golden two-lap run of the real F110Env + reference planner
+    e = g('env_laps.npz')
+    env = f110.F110Env(map=os.path.join(MAPS, 'example_map'), map_ext='.png', num_agents=1, timestep=0.01,
+                       scan_noise_std=0.0, num_envs=3, device=dev)
+    obs, rew, done, info = env.reset(np.repeat(e['pose0'][None], 3, axis=0))
+    T = e['actions'].shape[0]
+    worst = 0.0
+    for t in range(1, T):
+        act = pl.plan_actions(obs, 0.82461887897713965, 1.375)
+        obs, rew, done, info = env.step(act)
+        if t % 37 == 0 or t == T - 1:
+            st_ = cpu(env.sim.state)[:, 0]
+            worst = max(worst, np.abs(st_ - e['states'][t]).max())
+    assert worst < 1e-6, worst           # 3330 closed-loop ticks; planner + sim ulps do not amplify
+    assert bool(done.all()) and cpu(obs['lap_counts'])[0, 0] == 2.0
+    assert abs(cpu(obs['lap_times'])[0, 0] - e['lap_times'][-1][0]) < 1e-9

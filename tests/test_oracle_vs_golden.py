@@ -125,3 +125,24 @@ def test_env_laps(example_map):
         assert np.array_equal(sim.toggle_list, k['toggles'][t]), t
         assert done == bool(k['done'][t]), t
     assert done and sim.lap_counts[0] == 2.0
+
+
+def test_planner_vs_reference():
+    """oracle pure pursuit == reference PurePursuitPlanner.plan (examples/waypoint_follow.py) incl. the
+    re-acquire and no-waypoint branches; ulp-level slack for the BLAS dot products in the reference."""
+    k = g('kat_planner.npz')
+    wp = np.loadtxt(os.path.join(MAPS, 'example_waypoints.csv'), delimiter=';', skiprows=3)
+    wx, wy, wv = wp[:, 1].copy(), wp[:, 2].copy(), wp[:, 5].copy()
+    out = np.array([oracle.pure_pursuit(wx, wy, wv, p, float(k['tlad']), float(k['vgain']), float(k['wheelbase']))
+                    for p in k['poses']])
+    assert np.abs(out - k['speed_steer']).max() < 1e-12
+    none = (k['speed_steer'][:, 0] == 4.0) & (k['speed_steer'][:, 1] == 0.0)
+    assert 10 < none.sum() < 500
+    out2 = np.array([oracle.pure_pursuit(wx, wy, wv, p, 2.5, 0.9, float(k['wheelbase'])) for p in k['poses'][:400]])
+    assert np.abs(out2 - k['speed_steer_l25']).max() < 1e-12
+    # the env_laps golden is the same planner in closed loop: actions[t] = plan(state[t-1])
+    e = g('env_laps.npz')
+    for t in range(1, 400):
+        st = e['states'][t - 1]
+        sp, sa = oracle.pure_pursuit(wx, wy, wv, (st[0], st[1], st[4]), 0.82461887897713965, 1.375, 0.17145 + 0.15875)
+        assert abs(sa - e['actions'][t, 0, 0]) < 1e-12 and abs(sp - e['actions'][t, 0, 1]) < 1e-12

@@ -206,7 +206,8 @@ def run_b200(args):
     NA = N * A
     K, W = args.steps, args.warmup
 
-    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, SEED + rank, num_envs=N, num_beams=B, device=dev)
+    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, SEED + rank, num_envs=N, num_beams=B, device=dev,
+                         march_item_beams=int(os.environ.get('F110_MARCH_ITEM_BEAMS', '32')))
     sim.set_map(f110.maps.resolve_map_path('example_map'), '.png')
     wp_np = f110.maps.load_waypoints()
     wp = torch.from_numpy(wp_np).to(dev)

@@ -19,6 +19,7 @@
 #include "lidar.cuh"
 #include "march.cuh"
 #include "planner.cuh"
+#include "edt.cuh"
 
 namespace f110 {
 
@@ -104,8 +105,14 @@ __device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned w,
 }
 
 // ------------------------------------------------------------------------------------ k_dynamics
+struct FirstLookup {
+    const double *__restrict__ cells;    // dt / res, or NULL: not a fast-path map
+    double ox, oy, inv_res;
+    unsigned width, height, last;
+};
+
 __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
-                                                  double theta_dis_f, int dyn_blocks) {
+                                                  double theta_dis_f, int dyn_blocks, FirstLookup fl) {
     const int NA = s.num_envs * s.num_agents;
     if ((int)blockIdx.x >= dyn_blocks) {     // extra blocks: build the march work queue (block-uniform branch)
         build_march_order(s, (blockIdx.x - (unsigned)dyn_blocks) * blockDim.x + threadIdx.x,
@@ -140,9 +147,17 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
         sx = st[0] + s.lidar_dist * cos(st[4]);
         sy = st[1] + s.lidar_dist * sin(st[4]);
     }
+    // slot 2: on fast-path maps the DT value of the scan-pose cell in cell units — the first lookup of every
+    // beam of this agent (laser_models.py:129), done once here; otherwise the yaw
+    double slot2 = st[4];
+    if (fl.cells) {
+        CellConsts k;
+        k.ox = fl.ox; k.oy = fl.oy; k.eps = 0; k.tmax = 0; k.width = fl.width; k.height = fl.height; k.last = fl.last;
+        slot2 = __ldg(fl.cells + cell_index(sx * fl.inv_res, sy * fl.inv_res, k));
+    }
     double2 *sp = reinterpret_cast<double2 *>(s.scan_pose) + 2 * (size_t)a;
     sp[0] = make_double2(sx, sy);
-    sp[1] = make_double2(st[4], theta_index0(st[4], fov, theta_dis_f));
+    sp[1] = make_double2(slot2, theta_index0(st[4], fov, theta_dis_f));
     // pose snapshot (Simulator.agent_poses, base_classes.py:574) + cos/sin of the yaw: every vertex / heading
     // computation of the finalize kernel reuses them instead of re-evaluating fp64 trig per opponent
     double *ap = s.agent_poses + 5 * (size_t)a;
@@ -647,20 +662,20 @@ static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArg
     return F110_OK;
 }
 
-template <int PT>
+template <int PT, int SUB>
 static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned blocks, bool coded, bool noise, bool count,
                               cudaStream_t st) {
     if (k.trace) {
-        if (coded) k_march_persistent<true, false, false, true, PT><<<blocks, PT, 0, st>>>(k, mq);
-        else k_march_persistent<false, false, false, true, PT><<<blocks, PT, 0, st>>>(k, mq);
+        if (coded) k_march_persistent<true, false, false, true, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<false, false, false, true, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
     } else if (coded) {
-        if (count) k_march_persistent<true, false, true, false, PT><<<blocks, PT, 0, st>>>(k, mq);
-        else if (noise) k_march_persistent<true, true, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
-        else k_march_persistent<true, false, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+        if (count) k_march_persistent<true, false, true, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
+        else if (noise) k_march_persistent<true, true, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<true, false, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
     } else {
-        if (count) k_march_persistent<false, false, true, false, PT><<<blocks, PT, 0, st>>>(k, mq);
-        else if (noise) k_march_persistent<false, true, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
-        else k_march_persistent<false, false, false, false, PT><<<blocks, PT, 0, st>>>(k, mq);
+        if (count) k_march_persistent<false, false, true, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
+        else if (noise) k_march_persistent<false, true, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<false, false, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
     }
 }
 
@@ -722,18 +737,27 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
 
     if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
     const int variant = rm_variant();
+    // work-item width: march_ipa = ceil(B/32) -> one 32-beam slice per item, ceil(B/64) -> two
+    const int item_sub = (sim->march_ipa == (beams->num_beams + 31) / 32) ? 1
+                       : (sim->march_ipa == (beams->num_beams + 63) / 64) ? 2 : 0;
     const bool queued = sim->march_cost && sim->march_order && sim->march_count && variant != 7 &&
-                        sim->march_ipa == (beams->num_beams + 31) / 32 && sim->march_ipa <= 256 &&
+                        item_sub != 0 && sim->march_ipa <= 256 &&
                         (unsigned long long)NA < (1ull << 22) &&
                         map->fast_path && map->dt_cells && map->sincos && beams->cos_side;
     const int dyn_blocks = (NA + 127) / 128;
     const int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 127) / 128) : 0;
-    k_dynamics<<<dyn_blocks + order_blocks, 128, 0, st>>>(*sim, actions, beams->fov, (double)map->theta_dis, dyn_blocks);
+    const bool cell_march = map->fast_path && map->dt_cells && map->sincos && beams->cos_side &&
+                            (unsigned long long)map->width * (unsigned long long)map->height < (1ull << 32);
+    FirstLookup fl;
+    fl.cells = cell_march ? map->dt_cells : nullptr;
+    fl.inv_res = 1.0 / map->resolution; fl.ox = map->orig_x * fl.inv_res; fl.oy = map->orig_y * fl.inv_res;
+    fl.width = (unsigned)map->width; fl.height = (unsigned)map->height;
+    fl.last = (unsigned)map->width * (unsigned)map->height - 1u;
+    k_dynamics<<<dyn_blocks + order_blocks, 128, 0, st>>>(*sim, actions, beams->fov, (double)map->theta_dis, dyn_blocks, fl);
     LAUNCH_CHECK("k_dynamics");
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
 
-    if (map->fast_path && map->dt_cells && map->sincos && beams->cos_side && true &&
-        (unsigned long long)map->width * (unsigned long long)map->height < (1ull << 32)) {
+    if (cell_march) {
         MarchK k;
         const bool coded = map->dt_codes && map->dt_lut && variant == 6;   // measured: the fp64 table wins once issue-bound
         k.codes = map->dt_codes; k.lut = map->dt_lut; k.cells = map->dt_cells;
@@ -764,9 +788,9 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
             const unsigned blocks = (unsigned)num_sms() * 4u;
-            if (variant == 11) launch_persistent<448>(k, mq, blocks, coded, noise, count, st);
-            else if (variant == 12) launch_persistent<384>(k, mq, blocks, coded, noise, count, st);
-            else launch_persistent<512>(k, mq, blocks, coded, noise, count, st);
+            if (item_sub == 2) launch_persistent<512, 2>(k, mq, blocks, coded, noise, count, st);
+            else if (variant == 12) launch_persistent<384, 1>(k, mq, blocks, coded, noise, count, st);
+            else launch_persistent<512, 1>(k, mq, blocks, coded, noise, count, st);
         } else {
             const dim3 grid((unsigned)NA, (unsigned)bpa);
             if (variant == 9) launch_march<24>(k, grid, coded, noise, count, st);
@@ -1049,6 +1073,21 @@ int f110_pure_pursuit(const double *wx, const double *wy, const double *wv, int3
         wx, wy, wv, num_waypoints, pose_x, pose_y, pose_theta, M, lookahead_distance, vgain, wheelbase, max_reacquire,
         actions_out);
     LAUNCH_CHECK("k_pure_pursuit");
+    return F110_OK;
+}
+
+int f110_edt(const uint8_t *occupied, int32_t height, int32_t width, double resolution, int32_t *scratch, double *dt_out,
+             int64_t *k_out, void *stream) {
+    if (!occupied || !scratch || !dt_out || height <= 0 || width <= 0 || !(resolution > 0)) return F110_ERR_INVALID;
+    if ((size_t)width * sizeof(int32_t) > 200 * 1024) return F110_ERR_INVALID;      // one row of g must fit in shared memory
+    cudaStream_t st = (cudaStream_t)stream;
+    k_edt_columns<<<(width + 127) / 128, 128, 0, st>>>(occupied, height, width, scratch);
+    LAUNCH_CHECK("k_edt_columns");
+    const size_t smem = (size_t)width * sizeof(int32_t);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_edt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_edt_rows<<<height, 256, smem, st>>>(scratch, height, width, resolution, dt_out, k_out);
+    LAUNCH_CHECK("k_edt_rows");
     return F110_OK;
 }
 

@@ -19,7 +19,7 @@ struct MarchK {
     const double *__restrict__ cells;       // [H*W] dt / res
     const double2 *__restrict__ sincos;     // [theta_dis] (sin, cos)
     const double2 *__restrict__ cos_side;   // [B] (cos(scan_angle_i), side_distance_i)
-    const double2 *__restrict__ scan_pose;  // [M][2] (x, y), (yaw, theta_index0)
+    const double2 *__restrict__ scan_pose;  // [M][2] (x, y), (first lookup d0 in cells, theta_index0)
     const double *__restrict__ vel;         // [M]
     float *__restrict__ out;                // [M][B]
     int32_t *__restrict__ wall_flag;        // [M]
@@ -91,20 +91,21 @@ struct MarchQueue {
 
 // One beam: LUT heading, sphere tracing in cell units, optional noise, iTTC predicate, fp32 range out.
 // xy = scan position (m), ti0 = LUT index of beam 0, v = longitudinal velocity of the agent.
+// d0 = DT value (cell units) of the pose cell: the first lookup of every beam of the agent, done once per agent
+// by k_dynamics instead of once per beam here.
 template <bool CODED, bool NOISE>
-__device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, double2 xy, double ti0, double v,
-                                           unsigned &nlook) {
+__device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, double2 xy, double d0, double ti0,
+                                           double v, unsigned &nlook) {
     const int ti = beam_theta_index(ti0, i, p.inc, p.theta_dis_f, p.ti_guard);
     const double2 sc = __ldg(p.sincos + ti);
     double range;
     unsigned n = 0;
     if (fabs(xy.x) < 1e8 && fabs(xy.y) < 1e8) {
         const double MAGIC = 6755399441055744.0;   // 2^52 + 2^51: round-down add == floor in the low word
-        // T and D start at 0 so that the first pass of the loop is the pose-cell lookup (X + 0*c == X and
-        // 0 + D == D exactly): one loop body, no peeled copy of it in the instruction stream
-        double X = xy.x * p.inv_res, Y = xy.y * p.inv_res, T = 0.0, D = 0.0;
+        double X = xy.x * p.inv_res, Y = xy.y * p.inv_res, T = d0, D = d0;
+        n = 1;
 #pragma unroll 1
-        do {
+        while (D > p.eps && T <= p.tmax) {
             X = X + D * sc.y;
             Y = Y + D * sc.x;
             const int c = __double2loint(__dadd_rd(X - p.ox, MAGIC));
@@ -120,7 +121,7 @@ __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, d
             }
             T = T + D;
             n++;
-        } while (D > p.eps && T <= p.tmax);
+        }
         range = ((T > p.tmax) ? p.tmax : T) * p.res;
     } else {
         range = march_generic(p.dt, p.orig_x, p.orig_y, p.x_max, p.y_max, p.res, p.dt_oob, p.eps_m, p.max_range,
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
     {
         const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
         const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
-        march_beam<CODED, NOISE>(p, a, i, xy, yt.y, __ldg(p.vel + a), nlook);
+        march_beam<CODED, NOISE>(p, a, i, xy, yt.x, yt.y, __ldg(p.vel + a), nlook);
     }
     if (p.trace || COUNT) {
         const unsigned act = __activemask();
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
 
 // persistent: gridDim.x blocks of 512 threads stay resident; queue position q = k * gridDim.x + blockIdx.x.
 // cost[] is indexed by the packed item id (agent << 8 | slice), so no multiply/divide is needed per item.
-template <bool CODED, bool NOISE, bool COUNT, bool TRACE, int PT>
+// SUB = 32-beam slices per work item (1 or 2): a wider item halves the per-item queue / pose / cost overhead
+template <bool CODED, bool NOISE, bool COUNT, bool TRACE, int PT, int SUB>
 __global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
     if (threadIdx.x == 0) s_next = 0u;
@@ -198,12 +200,18 @@ __global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, cons
         if (TRACE) t0 = gtime();
         const unsigned it = mq.order[(q < nA) ? q : (q < nAB) ? (mq.items + (q - nA)) : (2u * mq.items + (q - nAB))];
         const unsigned a = it >> 8;
-        const int i = (int)((it & 255u) * 32u + lane);
         const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
         const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
         const double v = __ldg(p.vel + a);
         unsigned nlook = 0;
-        if (i < p.B) march_beam<CODED, NOISE>(p, a, i, xy, yt.y, v, nlook);
+#pragma unroll 1
+        for (int sub = 0; sub < SUB; sub++) {
+            const int i = (int)(((it & 255u) * SUB + sub) * 32u + lane);
+            unsigned n1 = 0;
+            if (i < p.B) march_beam<CODED, NOISE>(p, a, i, xy, yt.x, yt.y, v, n1);
+            nlook = (SUB == 1) ? n1 : max(nlook, n1);
+            if (COUNT) looks += n1;
+        }
         const unsigned mx = __reduce_max_sync(0xffffffffu, nlook);
         if (lane == 0) {
             mq.cost[it] = mx;
@@ -212,7 +220,6 @@ __global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, cons
                 tr[0] = smid(); tr[1] = t0; tr[2] = gtime(); tr[3] = mx;
             }
         }
-        if (COUNT) looks += nlook;
     }
     if (COUNT) {
         const unsigned n = __reduce_add_sync(0xffffffffu, looks);

@@ -60,7 +60,10 @@ class DeviceMap(object):
                              nat.ptr(self.sincos))
 
     @classmethod
-    def from_yaml(cls, map_path, map_ext, device, **kw):
+    def from_yaml(cls, map_path, map_ext, device, edt='scipy', **kw):
+        """edt='scipy': the reference's host pipeline; edt='device': C ABI f110_edt (bit-identical table)."""
+        if edt == 'device':
+            return cls(hostmaps.load_map_device_edt(map_path, map_ext, device), device, **kw)
         return cls(hostmaps.load_map(map_path, map_ext), device, **kw)
 
 
@@ -95,7 +98,7 @@ class Simulator(object):
 
     def __init__(self, params, num_agents, seed, time_step=0.01, ego_idx=0, integrator=Integrator.RK4,
                  lidar_dist=0.0, num_envs=1, num_beams=1080, fov=4.7, device=None, noise_std=0.0,
-                 count_lookups=False, march_queue=True):
+                 count_lookups=False, march_queue=True, march_item_beams=32):
         nat.lib()   # fail loudly right away if the CUDA library is missing
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
@@ -147,7 +150,9 @@ class Simulator(object):
         self.lookup_counter = torch.zeros((1,), dtype=torch.int64, device=dev) if count_lookups else None
         self.tick_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
         # work queue of the persistent ray-march kernel (csrc/march.cuh): last tick's heavy items go first
-        self.march_ipa = (B + 31) // 32 if (march_queue and (B + 31) // 32 <= 256) else 0
+        ib = int(march_item_beams)
+        assert ib in (32, 64)
+        self.march_ipa = (B + ib - 1) // ib if (march_queue and (B + ib - 1) // ib <= 256) else 0
         items = NA * self.march_ipa
         self.march_cost = torch.full((NA * 256,), -1, **i32) if self.march_ipa else None
         self.march_order = torch.zeros((3, items), **i32) if self.march_ipa else None
@@ -170,9 +175,10 @@ class Simulator(object):
         self._graph = None
 
     # ------------------------------------------------------------------ configuration
-    def set_map(self, map_path, map_ext):
-        """base_classes.py:499-511 / laser_models.py:383-427 (load-time: PIL + yaml + scipy EDT on host)."""
-        self.set_device_map(DeviceMap.from_yaml(map_path, map_ext, self.device))
+    def set_map(self, map_path, map_ext, edt='scipy'):
+        """base_classes.py:499-511 / laser_models.py:383-427 (load-time: PIL + yaml + EDT; edt='device' runs the
+        exact distance transform on the GPU instead of scipy on the host)."""
+        self.set_device_map(DeviceMap.from_yaml(map_path, map_ext, self.device, edt=edt))
 
     def set_device_map(self, device_map):
         self.map = device_map

@@ -78,7 +78,7 @@ typedef struct {
     double *state;                  /* [F110_NSTATE][N*A] */
     double *steer_buf;              /* [2][N*A]   steering delay FIFO, row 0 = newest (base_classes.py:270-278) */
     int32_t *steer_cnt;             /* [N*A] */
-    double *scan_pose;              /* [N*A][4]   (scan_x, scan_y, yaw, theta_index0) written by the dynamics kernel */
+    double *scan_pose;              /* [N*A][4]   (scan_x, scan_y, first DT lookup in cells | yaw, theta_index0): dynamics -> march */
     double *agent_poses;            /* [N*A][5]   Simulator.agent_poses snapshot (base_classes.py:574): x, y, yaw, cos yaw, sin yaw */
     float *scans;                   /* [N*A][num_beams] */
     int32_t *wall_flag;             /* [N*A]      RaceCar.in_collision (iTTC) */
@@ -98,7 +98,7 @@ typedef struct {
                                              and the auto-reset draw so that CUDA-graph replays stay distinct */
     /* optional work queue of the persistent ray-march kernel (csrc/march.cuh): 32-beam items, last tick's
        heavy items first.  Results never depend on it.  All NULL/0 = off (one block per 64-beam tile instead).
-       I = N*A*march_ipa items, march_ipa = ceil(num_beams/32) <= 256. */
+       I = N*A*march_ipa items; march_ipa = ceil(num_beams/32) (32-beam items) or ceil(num_beams/64) (64-beam items), <= 256. */
     uint32_t *march_cost;           /* [N*A*256] indexed by (agent << 8 | item); initialised to 0xFFFFFFFF (= unknown) */
     uint32_t *march_order;          /* [3][I]  */
     uint32_t *march_count;          /* [4]     zero-initialised by the caller */
@@ -210,6 +210,13 @@ int f110_scan_noise(float *scans, int64_t count, double std_dev, uint64_t seed, 
 int f110_pure_pursuit(const double *wx, const double *wy, const double *wv, int32_t num_waypoints, const double *pose_x,
                       const double *pose_y, const double *pose_theta, int32_t M, double lookahead_distance, double vgain,
                       double wheelbase, double max_reacquire, double *actions_out, void *stream);
+
+/* Exact Euclidean distance transform on the device (load-time; reference laser_models.py:40-53 get_dt =
+ * resolution * scipy.ndimage.distance_transform_edt(bitmap)): occupied [H][W] u8 (1 where the thresholded image
+ * is 0), scratch [H][W] i32, dt_out [H][W] f64 = resolution * sqrt(k) with k the exact squared cell distance
+ * (optionally written to k_out [H][W] i64).  Bit-identical to the scipy table. */
+int f110_edt(const uint8_t *occupied, int32_t height, int32_t width, double resolution, int32_t *scratch, double *dt_out,
+             int64_t *k_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -462,3 +462,23 @@ def test_planner_vs_reference_and_closed_loop(f110, dev, example_map):
     assert worst < 1e-6, worst           # 3330 closed-loop ticks; planner + sim ulps do not amplify
     assert bool(done.all()) and cpu(obs['lap_counts'])[0, 0] == 2.0
     assert abs(cpu(obs['lap_times'])[0, 0] - e['lap_times'][-1][0]) < 1e-9
+
+
+@pytest.mark.parametrize('name', ['example_map', 'berlin', 'skirk', 'vegas', 'stata_basement'])
+def test_device_edt_matches_scipy(f110, dev, name):
+    """f110_edt == resolution * scipy.ndimage.distance_transform_edt, bit for bit (laser_models.py:40-53)."""
+    from scipy.ndimage import distance_transform_edt as edt
+    img, res, origin = f110.maps.load_bitmap(f110.maps.resolve_map_path(name), '.png')
+    got = cpu(f110.maps.device_edt(img, res, dev))
+    assert np.array_equal(got, res * edt(img))
+
+
+def test_update_map_with_device_edt(f110, dev):
+    k = g('scans_berlin.npz')
+    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, 1, 0, num_envs=k['poses'].shape[0], device=dev)
+    sim.set_map(f110.maps.resolve_map_path('example_map'), '.png')
+    sim.set_map(f110.maps.resolve_map_path('berlin'), '.png', edt='device')       # F110Env.update_map path
+    sim.reset(k['poses'][:, None, :])
+    # a zero-action tick from rest leaves the pose unchanged, so the scans are those of the golden poses
+    obs = sim.step(np.zeros((k['poses'].shape[0], 1, 2)))
+    assert np.abs(cpu(obs['scans'])[:, 0].astype(np.float64) - k['scan_1080']).max() < TOL_SCAN32

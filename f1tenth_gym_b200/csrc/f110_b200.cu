@@ -106,9 +106,11 @@ __device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned w,
 
 // ------------------------------------------------------------------------------------ k_dynamics
 struct FirstLookup {
-    const double *__restrict__ cells;    // dt / res, or NULL: not a fast-path map
-    double ox, oy, inv_res;
+    const double *__restrict__ cells;    // dt / res (cell units) or dt (metres), or NULL: generic march kernel
+    double ox, oy, inv_res;              // cell units
+    double res, orig_x, orig_y, x_max, y_max;   // metres
     unsigned width, height, last;
+    int metres;
 };
 
 __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
@@ -150,10 +152,16 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
     // slot 2: on fast-path maps the DT value of the scan-pose cell in cell units — the first lookup of every
     // beam of this agent (laser_models.py:129), done once here; otherwise the yaw
     double slot2 = st[4];
-    if (fl.cells) {
+    if (fl.cells && !fl.metres) {
         CellConsts k;
         k.ox = fl.ox; k.oy = fl.oy; k.eps = 0; k.tmax = 0; k.width = fl.width; k.height = fl.height; k.last = fl.last;
         slot2 = __ldg(fl.cells + cell_index(sx * fl.inv_res, sy * fl.inv_res, k));
+    } else if (fl.cells) {          // literal xy_2_rc (laser_models.py:55-86), unrotated origin
+        const double tx = sx - fl.orig_x, ty = sy - fl.orig_y;
+        unsigned idx = fl.last;
+        if (!(tx < 0 || tx >= fl.x_max || ty < 0 || ty >= fl.y_max))
+            idx = (unsigned)(int)(ty / fl.res) * fl.width + (unsigned)(int)(tx / fl.res);
+        slot2 = __ldg(fl.cells + idx);
     }
     double2 *sp = reinterpret_cast<double2 *>(s.scan_pose) + 2 * (size_t)a;
     sp[0] = make_double2(sx, sy);
@@ -662,33 +670,33 @@ static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArg
     return F110_OK;
 }
 
-template <int PT, int SUB>
+template <int PT, int SUB, bool CELLS>
 static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned blocks, bool coded, bool noise, bool count,
                               cudaStream_t st) {
     if (k.trace) {
-        if (coded) k_march_persistent<true, false, false, true, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
-        else k_march_persistent<false, false, false, true, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
-    } else if (coded) {
-        if (count) k_march_persistent<true, false, true, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
-        else if (noise) k_march_persistent<true, true, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
-        else k_march_persistent<true, false, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
+        if (coded && CELLS) k_march_persistent<CELLS, false, false, true, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<false, false, false, true, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
+    } else if (coded && CELLS) {
+        if (count) k_march_persistent<CELLS, false, true, false, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
+        else if (noise) k_march_persistent<CELLS, true, false, false, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<CELLS, false, false, false, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
     } else {
-        if (count) k_march_persistent<false, false, true, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
-        else if (noise) k_march_persistent<false, true, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
-        else k_march_persistent<false, false, false, false, PT, SUB><<<blocks, PT, 0, st>>>(k, mq);
+        if (count) k_march_persistent<false, false, true, false, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
+        else if (noise) k_march_persistent<false, true, false, false, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
+        else k_march_persistent<false, false, false, false, PT, SUB, CELLS><<<blocks, PT, 0, st>>>(k, mq);
     }
 }
 
-template <int MINB>
+template <int MINB, bool CELLS>
 static void launch_march(const MarchK &k, dim3 grid, bool coded, bool noise, bool count, cudaStream_t st) {
-    if (coded) {
-        if (count) k_march<true, false, true, MINB><<<grid, 64, 0, st>>>(k);
-        else if (noise) k_march<true, true, false, MINB><<<grid, 64, 0, st>>>(k);
-        else k_march<true, false, false, MINB><<<grid, 64, 0, st>>>(k);
+    if (coded && CELLS) {
+        if (count) k_march<CELLS, false, true, MINB, CELLS><<<grid, 64, 0, st>>>(k);
+        else if (noise) k_march<CELLS, true, false, MINB, CELLS><<<grid, 64, 0, st>>>(k);
+        else k_march<CELLS, false, false, MINB, CELLS><<<grid, 64, 0, st>>>(k);
     } else {
-        if (count) k_march<false, false, true, MINB><<<grid, 64, 0, st>>>(k);
-        else if (noise) k_march<false, true, false, MINB><<<grid, 64, 0, st>>>(k);
-        else k_march<false, false, false, MINB><<<grid, 64, 0, st>>>(k);
+        if (count) k_march<false, false, true, MINB, CELLS><<<grid, 64, 0, st>>>(k);
+        else if (noise) k_march<false, true, false, MINB, CELLS><<<grid, 64, 0, st>>>(k);
+        else k_march<false, false, false, MINB, CELLS><<<grid, 64, 0, st>>>(k);
     }
 }
 
@@ -743,13 +751,20 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     const bool queued = sim->march_cost && sim->march_order && sim->march_count && variant != 7 &&
                         item_sub != 0 && sim->march_ipa <= 256 &&
                         (unsigned long long)NA < (1ull << 22) &&
-                        map->fast_path && map->dt_cells && map->sincos && beams->cos_side;
+                        map->orig_c == 1.0 && map->orig_s == 0.0 && map->sincos && beams->cos_side && variant != 13;
     const int dyn_blocks = (NA + 127) / 128;
     const int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 127) / 128) : 0;
-    const bool cell_march = map->fast_path && map->dt_cells && map->sincos && beams->cos_side &&
-                            (unsigned long long)map->width * (unsigned long long)map->height < (1ull << 32);
+    // the lean march kernels need an unrotated map origin and the interleaved tables; cell units additionally a
+    // power-of-two resolution (fast_path) and the cell-unit table
+    const bool cell_march = map->orig_c == 1.0 && map->orig_s == 0.0 && map->sincos && beams->cos_side &&
+                            (unsigned long long)map->width * (unsigned long long)map->height < (1ull << 32) &&
+                            variant != 13;
+    const bool cell_units = cell_march && map->fast_path && map->dt_cells;
     FirstLookup fl;
-    fl.cells = cell_march ? map->dt_cells : nullptr;
+    fl.cells = cell_march ? (cell_units ? map->dt_cells : map->dt) : nullptr;
+    fl.metres = cell_units ? 0 : 1;
+    fl.res = map->resolution; fl.orig_x = map->orig_x; fl.orig_y = map->orig_y;
+    fl.x_max = mv.x_max; fl.y_max = mv.y_max;
     fl.inv_res = 1.0 / map->resolution; fl.ox = map->orig_x * fl.inv_res; fl.oy = map->orig_y * fl.inv_res;
     fl.width = (unsigned)map->width; fl.height = (unsigned)map->height;
     fl.last = (unsigned)map->width * (unsigned)map->height - 1u;
@@ -759,7 +774,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
 
     if (cell_march) {
         MarchK k;
-        const bool coded = map->dt_codes && map->dt_lut && variant == 6;   // measured: the fp64 table wins once issue-bound
+        const bool coded = cell_units && map->dt_codes && map->dt_lut && variant == 6;   // measured: the fp64 table wins once issue-bound
         k.codes = map->dt_codes; k.lut = map->dt_lut; k.cells = map->dt_cells;
         k.sincos = reinterpret_cast<const double2 *>(map->sincos);
         k.cos_side = reinterpret_cast<const double2 *>(beams->cos_side);
@@ -788,13 +803,14 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
             const unsigned blocks = (unsigned)num_sms() * 4u;
-            if (item_sub == 2) launch_persistent<512, 2>(k, mq, blocks, coded, noise, count, st);
-            else if (variant == 12) launch_persistent<384, 1>(k, mq, blocks, coded, noise, count, st);
-            else launch_persistent<512, 1>(k, mq, blocks, coded, noise, count, st);
+            if (!cell_units) launch_persistent<512, 1, false>(k, mq, blocks, coded, noise, count, st);
+            else if (item_sub == 2) launch_persistent<512, 2, true>(k, mq, blocks, coded, noise, count, st);
+            else launch_persistent<512, 1, true>(k, mq, blocks, coded, noise, count, st);
         } else {
             const dim3 grid((unsigned)NA, (unsigned)bpa);
-            if (variant == 9) launch_march<24>(k, grid, coded, noise, count, st);
-            else launch_march<32>(k, grid, coded, noise, count, st);
+            if (!cell_units) launch_march<32, false>(k, grid, coded, noise, count, st);
+            else if (variant == 9) launch_march<24, true>(k, grid, coded, noise, count, st);
+            else launch_march<32, true>(k, grid, coded, noise, count, st);
         }
         LAUNCH_CHECK("k_march");
         if (count && noise) return F110_ERR_INVALID;   // counting runs are noise-free by construction

@@ -93,14 +93,41 @@ struct MarchQueue {
 // xy = scan position (m), ti0 = LUT index of beam 0, v = longitudinal velocity of the agent.
 // d0 = DT value (cell units) of the pose cell: the first lookup of every beam of the agent, done once per agent
 // by k_dynamics instead of once per beam here.
-template <bool CODED, bool NOISE>
+// CELLS = true : resolution 2^-k — march in cell units (see lidar.cuh), d0 / table in cells.
+// CELLS = false: any resolution, unrotated origin — march in metres on the reference's own table; the cell index
+//   needs RN(t/res) exactly as the reference's `int(x_rot/resolution)` computes it.  With inv = RN(1/res) from the
+//   host, q = t*inv; y = fma(fma(-q, res, t), inv, q) is the correctly rounded quotient (the residual-correction
+//   tail of the IEEE division algorithm, 3 instructions instead of the ~10 of a full fp64 divide).
+template <bool CODED, bool NOISE, bool CELLS>
 __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, double2 xy, double d0, double ti0,
                                            double v, unsigned &nlook) {
     const int ti = beam_theta_index(ti0, i, p.inc, p.theta_dis_f, p.ti_guard);
     const double2 sc = __ldg(p.sincos + ti);
     double range;
     unsigned n = 0;
-    if (fabs(xy.x) < 1e8 && fabs(xy.y) < 1e8) {
+    if (!CELLS && fabs(xy.x) < 1e8 && fabs(xy.y) < 1e8) {
+        const double MAGIC = 6755399441055744.0;
+        double X = xy.x, Y = xy.y, T = d0, D = d0;
+        n = 1;
+#pragma unroll 1
+        while (D > p.eps_m && T <= p.max_range) {
+            X = X + D * sc.y;
+            Y = Y + D * sc.x;
+            const double tx = X - p.orig_x, ty = Y - p.orig_y;
+            double qx = tx * p.inv_res, qy = ty * p.inv_res;
+            qx = __fma_rn(__fma_rn(-qx, p.res, tx), p.inv_res, qx);
+            qy = __fma_rn(__fma_rn(-qy, p.res, ty), p.inv_res, qy);
+            const int c = __double2loint(__dadd_rd(qx, MAGIC));     // floor == int() for the in-bounds quotients
+            const int r = __double2loint(__dadd_rd(qy, MAGIC));
+            unsigned idx = (unsigned)r * p.width + (unsigned)c;
+            // laser_models.py:79: x_rot < 0 or x_rot >= width*resolution (the fp64 product) -> dt[-1,-1]
+            if ((unsigned)c >= p.width || (unsigned)r >= p.height || tx >= p.x_max || ty >= p.y_max) idx = p.last;
+            D = __ldg(p.dt + idx);
+            T = T + D;
+            n++;
+        }
+        range = (T > p.max_range) ? p.max_range : T;
+    } else if (CELLS && fabs(xy.x) < 1e8 && fabs(xy.y) < 1e8) {
         const double MAGIC = 6755399441055744.0;   // 2^52 + 2^51: round-down add == floor in the low word
         double X = xy.x * p.inv_res, Y = xy.y * p.inv_res, T = d0, D = d0;
         n = 1;
@@ -148,7 +175,7 @@ __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, d
 }
 
 // grid (agents, 64-beam tiles per agent), 64 threads: one tile of one agent per block (no queue)
-template <bool CODED, bool NOISE, bool COUNT, int MINB>
+template <bool CODED, bool NOISE, bool COUNT, int MINB, bool CELLS>
 __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
     unsigned long long t0 = 0;
     if (p.trace) t0 = gtime();
@@ -159,7 +186,7 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
     {
         const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
         const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
-        march_beam<CODED, NOISE>(p, a, i, xy, yt.x, yt.y, __ldg(p.vel + a), nlook);
+        march_beam<CODED, NOISE, CELLS>(p, a, i, xy, yt.x, yt.y, __ldg(p.vel + a), nlook);
     }
     if (p.trace || COUNT) {
         const unsigned act = __activemask();
@@ -180,7 +207,7 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
 // persistent: gridDim.x blocks of 512 threads stay resident; queue position q = k * gridDim.x + blockIdx.x.
 // cost[] is indexed by the packed item id (agent << 8 | slice), so no multiply/divide is needed per item.
 // SUB = 32-beam slices per work item (1 or 2): a wider item halves the per-item queue / pose / cost overhead
-template <bool CODED, bool NOISE, bool COUNT, bool TRACE, int PT, int SUB>
+template <bool CODED, bool NOISE, bool COUNT, bool TRACE, int PT, int SUB, bool CELLS>
 __global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
     if (threadIdx.x == 0) s_next = 0u;
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, cons
         for (int sub = 0; sub < SUB; sub++) {
             const int i = (int)(((it & 255u) * SUB + sub) * 32u + lane);
             unsigned n1 = 0;
-            if (i < p.B) march_beam<CODED, NOISE>(p, a, i, xy, yt.x, yt.y, v, n1);
+            if (i < p.B) march_beam<CODED, NOISE, CELLS>(p, a, i, xy, yt.x, yt.y, v, n1);
             nlook = (SUB == 1) ? n1 : max(nlook, n1);
             if (COUNT) looks += n1;
         }

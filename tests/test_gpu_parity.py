@@ -482,3 +482,43 @@ def test_update_map_with_device_edt(f110, dev):
     # a zero-action tick from rest leaves the pose unchanged, so the scans are those of the golden poses
     obs = sim.step(np.zeros((k['poses'].shape[0], 1, 2)))
     assert np.abs(cpu(obs['scans'])[:, 0].astype(np.float64) - k['scan_1080']).max() < TOL_SCAN32
+
+
+@pytest.mark.parametrize('name', ['berlin', 'vegas', 'stata_basement'])
+def test_rollout_other_maps_vs_oracle(f110, dev, name):
+    """0.05 / 0.0504 m maps run the metre-unit persistent march (exact RN(t/res) through the FMA residual
+    correction): state, scans, collisions and the number of DT lookups must equal the oracle's."""
+    import oracle
+    dmap = f110.DeviceMap.from_yaml(f110.maps.resolve_map_path(name), '.png', dev)
+    assert dmap.host.fast_path == 0
+    h = dmap.host
+    omap = oracle.OracleMap(h.dt, h.resolution, (h.orig_x, h.orig_y, 0.0))
+    rng = np.random.default_rng(hash(name) % 1000)
+    N, A, T = 16, 2, 60
+    free = np.argwhere(h.dt > 0.6)
+    sel = free[rng.choice(free.shape[0], N, replace=False)]
+    poses = np.zeros((N, A, 3))
+    poses[:, 0, 0] = sel[:, 1] * h.resolution + h.orig_x + 0.011
+    poses[:, 0, 1] = sel[:, 0] * h.resolution + h.orig_y + 0.017
+    poses[:, 0, 2] = rng.uniform(0, 2 * np.pi, N)
+    poses[:, 1] = poses[:, 0] + np.array([0.45, 0.1, 0.3])          # a close second car: GJK + occlusion live
+    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev, count_lookups=True)
+    sim.set_device_map(dmap)
+    sim.reset(poses)
+    osims = [oracle.OracleSim(omap, num_agents=A) for _ in range(N)]
+    for e in range(N):
+        osims[e].reset(poses[e])
+    worst_state = worst_scan = 0.0
+    for t in range(T):
+        act = np.stack([rng.uniform(-0.4189, 0.4189, (N, A)), rng.uniform(0, 6, (N, A))], axis=2)
+        obs = sim.step(act)
+        st = cpu(sim.state).reshape(7, N, A).transpose(1, 2, 0)
+        sc = cpu(obs['scans']).astype(np.float64)
+        col = cpu(obs['collisions'])
+        for e in range(N):
+            osims[e].step(act[e])
+            worst_state = max(worst_state, np.abs(st[e] - osims[e].state).max())
+            worst_scan = max(worst_scan, np.abs(sc[e] - osims[e].scans).max())
+            assert np.array_equal(col[e], osims[e].collisions), (t, e)
+    assert worst_state < TOL_STATE and worst_scan < TOL_SCAN32, (worst_state, worst_scan)
+    assert sim.lookups() == sum(o.nlook for o in osims)

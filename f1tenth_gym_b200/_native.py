@@ -25,7 +25,7 @@ class F110Map(C.Structure):
                 ('theta_dis', C.c_int32), ('fast_path', C.c_int32),
                 ('dt_oob', C.c_double),
                 ('dt', _dp), ('dt_cells', _dp), ('dt_codes', _dp), ('dt_lut', _dp),
-                ('sines', _dp), ('cosines', _dp), ('sincos', _dp)]
+                ('sines', _dp), ('cosines', _dp), ('sincos', _dp), ('num_layers', C.c_int32)]
 
 
 class F110Beams(C.Structure):
@@ -36,7 +36,7 @@ class F110Beams(C.Structure):
 
 class F110Sim(C.Structure):
     _fields_ = [('num_envs', C.c_int32), ('num_agents', C.c_int32), ('integrator', C.c_int32),
-                ('ego_idx', C.c_int32),
+                ('ego_idx', C.c_int32), ('params_per_env', C.c_int32),
                 ('timestep', C.c_double), ('lidar_dist', C.c_double), ('ttc_thresh', C.c_double),
                 ('sim_length', C.c_double), ('sim_width', C.c_double),
                 ('params', _dp), ('state', _dp), ('steer_buf', _dp), ('steer_cnt', _dp),
@@ -44,7 +44,7 @@ class F110Sim(C.Structure):
                 ('collisions', _dp), ('collision_idx', _dp),
                 ('current_time', _dp), ('lap_times', _dp), ('lap_counts', _dp), ('toggle_list', _dp),
                 ('near_starts', _dp), ('start_xs', _dp), ('start_ys', _dp), ('start_thetas', _dp),
-                ('start_rot', _dp), ('done', _dp), ('checkpoint_done', _dp), ('env_arrivals', _dp),
+                ('start_rot', _dp), ('done', _dp), ('checkpoint_done', _dp), ('env_arrivals', _dp), ('env_layer', _dp),
                 ('lookup_counter', _dp), ('tick_counter', _dp),
                 ('march_cost', _dp), ('march_order', _dp), ('march_count', _dp), ('march_ipa', C.c_int32),
                 ('noise_std', C.c_double), ('noise_seed', C.c_uint64)]

@@ -111,6 +111,8 @@ struct FirstLookup {
     double res, orig_x, orig_y, x_max, y_max;   // metres
     unsigned width, height, last;
     int metres;
+    const int32_t *__restrict__ env_layer;   // multi-map batches: layer of each env, or NULL
+    unsigned long long layer_stride;
 };
 
 __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
     // the tick counter advances once per tick, here, before any kernel of the tick reads it (noise stream id,
     // auto-reset draw); nothing else in this kernel uses it
     if (a == 0 && s.tick_counter) *s.tick_counter += 1ull;
-    const double *p = s.params + (size_t)(a % s.num_agents) * F110_NPARAM;
+    const double *p = s.params + (size_t)(s.params_per_env ? a : a % s.num_agents) * F110_NPARAM;
     double st[7];
 #pragma unroll
     for (int k = 0; k < 7; k++) st[k] = s.state[(size_t)k * NA + a];
@@ -152,16 +154,17 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
     // slot 2: on fast-path maps the DT value of the scan-pose cell in cell units — the first lookup of every
     // beam of this agent (laser_models.py:129), done once here; otherwise the yaw
     double slot2 = st[4];
+    const size_t lo = fl.env_layer ? (size_t)fl.env_layer[a / s.num_agents] * (size_t)fl.layer_stride : (size_t)0;
     if (fl.cells && !fl.metres) {
         CellConsts k;
         k.ox = fl.ox; k.oy = fl.oy; k.eps = 0; k.tmax = 0; k.width = fl.width; k.height = fl.height; k.last = fl.last;
-        slot2 = __ldg(fl.cells + cell_index(sx * fl.inv_res, sy * fl.inv_res, k));
+        slot2 = __ldg(fl.cells + lo + cell_index(sx * fl.inv_res, sy * fl.inv_res, k));
     } else if (fl.cells) {          // literal xy_2_rc (laser_models.py:55-86), unrotated origin
         const double tx = sx - fl.orig_x, ty = sy - fl.orig_y;
         unsigned idx = fl.last;
         if (!(tx < 0 || tx >= fl.x_max || ty < 0 || ty >= fl.y_max))
             idx = (unsigned)(int)(ty / fl.res) * fl.width + (unsigned)(int)(tx / fl.res);
-        slot2 = __ldg(fl.cells + idx);
+        slot2 = __ldg(fl.cells + lo + idx);
     }
     double2 *sp = reinterpret_cast<double2 *>(s.scan_pose) + 2 * (size_t)a;
     sp[0] = make_double2(sx, sy);
@@ -280,7 +283,7 @@ __device__ __forceinline__ void finalize_agent(const f110_sim &s, const BeamView
 
     // ray_cast_agents (:206-227): opponents in ascending index, each bounded to its blocked-view window
     if (A > 1) {
-        const double *p = s.params + (size_t)slot * F110_NPARAM;
+        const double *p = s.params + (size_t)(s.params_per_env ? a : slot) * F110_NPARAM;
         const double length = p[P_LENGTH], width = p[P_WIDTH];
         float *scan = s.scans + (size_t)a * bv.num_beams;
         // an opponent whose nearest point is farther than any range the scan can hold (max_range plus noise
@@ -765,6 +768,10 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     fl.metres = cell_units ? 0 : 1;
     fl.res = map->resolution; fl.orig_x = map->orig_x; fl.orig_y = map->orig_y;
     fl.x_max = mv.x_max; fl.y_max = mv.y_max;
+    const bool layered = map->num_layers > 1 && sim->env_layer;
+    if (map->num_layers > 1 && !cell_march) return F110_ERR_INVALID;     // stacked maps need the lean march kernels
+    fl.env_layer = layered ? sim->env_layer : nullptr;
+    fl.layer_stride = (unsigned long long)map->width * (unsigned long long)map->height;
     fl.inv_res = 1.0 / map->resolution; fl.ox = map->orig_x * fl.inv_res; fl.oy = map->orig_y * fl.inv_res;
     fl.width = (unsigned)map->width; fl.height = (unsigned)map->height;
     fl.last = (unsigned)map->width * (unsigned)map->height - 1u;
@@ -774,7 +781,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
 
     if (cell_march) {
         MarchK k;
-        const bool coded = cell_units && map->dt_codes && map->dt_lut && variant == 6;   // measured: the fp64 table wins once issue-bound
+        const bool coded = cell_units && !layered && map->dt_codes && map->dt_lut && variant == 6;   // measured: the fp64 table wins once issue-bound
         k.codes = map->dt_codes; k.lut = map->dt_lut; k.cells = map->dt_cells;
         k.sincos = reinterpret_cast<const double2 *>(map->sincos);
         k.cos_side = reinterpret_cast<const double2 *>(beams->cos_side);
@@ -792,6 +799,8 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
         k.width = (unsigned)map->width; k.height = (unsigned)map->height;
         k.last = (unsigned)map->width * (unsigned)map->height - 1u;
         k.B = beams->num_beams;
+        k.env_layer = layered ? sim->env_layer : nullptr;
+        k.layer_stride = fl.layer_stride; k.num_agents = (unsigned)sim->num_agents;
         k.trace = g_trace;
         k.dt = map->dt; k.orig_x = map->orig_x; k.orig_y = map->orig_y; k.x_max = mv.x_max; k.y_max = mv.y_max;
         k.dt_oob = map->dt_oob; k.eps_m = map->eps; k.max_range = map->max_range;

@@ -33,6 +33,9 @@ struct MarchK {
     unsigned long long noise_seed;
     unsigned width, height, last;
     int B;
+    const int32_t *__restrict__ env_layer;  // [num_envs] map layer of each env, or NULL (single map)
+    unsigned long long layer_stride;        // H*W elements between layers of cells / dt
+    unsigned num_agents;
     unsigned long long *trace;              // debug: [blocks][4] (smid, t_start_ns, t_end_ns, warp-max steps) or NULL
     const double *__restrict__ dt;          // fp64 DT in metres + metadata: literal-arithmetic fallback
     double orig_x, orig_y, x_max, y_max, dt_oob, eps_m, max_range;
@@ -98,9 +101,14 @@ struct MarchQueue {
 //   needs RN(t/res) exactly as the reference's `int(x_rot/resolution)` computes it.  With inv = RN(1/res) from the
 //   host, q = t*inv; y = fma(fma(-q, res, t), inv, q) is the correctly rounded quotient (the residual-correction
 //   tail of the IEEE division algorithm, 3 instructions instead of the ~10 of a full fp64 divide).
+// element offset of agent a's map layer inside the stacked DT tables (multi-map batches share one canvas)
+__device__ __forceinline__ size_t layer_offset(const MarchK &p, unsigned a) {
+    return p.env_layer ? (size_t)p.env_layer[a / p.num_agents] * (size_t)p.layer_stride : (size_t)0;
+}
+
 template <bool CODED, bool NOISE, bool CELLS>
 __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, double2 xy, double d0, double ti0,
-                                           double v, unsigned &nlook) {
+                                           double v, size_t lo, unsigned &nlook) {
     const int ti = beam_theta_index(ti0, i, p.inc, p.theta_dis_f, p.ti_guard);
     const double2 sc = __ldg(p.sincos + ti);
     double range;
@@ -122,7 +130,7 @@ __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, d
             unsigned idx = (unsigned)r * p.width + (unsigned)c;
             // laser_models.py:79: x_rot < 0 or x_rot >= width*resolution (the fp64 product) -> dt[-1,-1]
             if ((unsigned)c >= p.width || (unsigned)r >= p.height || tx >= p.x_max || ty >= p.y_max) idx = p.last;
-            D = __ldg(p.dt + idx);
+            D = __ldg(p.dt + lo + idx);
             T = T + D;
             n++;
         }
@@ -140,18 +148,18 @@ __device__ __forceinline__ void march_beam(const MarchK &p, unsigned a, int i, d
             unsigned idx = (unsigned)r * p.width + (unsigned)c;
             if ((unsigned)c >= p.width || (unsigned)r >= p.height) idx = p.last;   // off-map reads dt[-1,-1]
             if (CODED) {
-                const unsigned code = __ldg(p.codes + idx);
-                if (code == 255u) D = escape_load(p.cells, idx);
+                const unsigned code = __ldg(p.codes + lo + idx);
+                if (code == 255u) D = escape_load(p.cells + lo, idx);
                 else D = __ldg(p.lut + code);
             } else {
-                D = __ldg(p.cells + idx);
+                D = __ldg(p.cells + lo + idx);
             }
             T = T + D;
             n++;
         }
         range = ((T > p.tmax) ? p.tmax : T) * p.res;
     } else {
-        range = march_generic(p.dt, p.orig_x, p.orig_y, p.x_max, p.y_max, p.res, p.dt_oob, p.eps_m, p.max_range,
+        range = march_generic(p.dt + lo, p.orig_x, p.orig_y, p.x_max, p.y_max, p.res, __ldg(p.dt + lo + p.last), p.eps_m, p.max_range,
                               (int)p.width, xy.x, xy.y, sc.x, sc.y);
         n = 1;
     }
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(64, MINB) k_march(const MarchK p) {
     {
         const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
         const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
-        march_beam<CODED, NOISE, CELLS>(p, a, i, xy, yt.x, yt.y, __ldg(p.vel + a), nlook);
+        march_beam<CODED, NOISE, CELLS>(p, a, i, xy, yt.x, yt.y, __ldg(p.vel + a), layer_offset(p, a), nlook);
     }
     if (p.trace || COUNT) {
         const unsigned act = __activemask();
@@ -230,12 +238,13 @@ __global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, cons
         const double2 xy = __ldg(p.scan_pose + 2 * (size_t)a);
         const double2 yt = __ldg(p.scan_pose + 2 * (size_t)a + 1);
         const double v = __ldg(p.vel + a);
+        const size_t lo = layer_offset(p, a);
         unsigned nlook = 0;
 #pragma unroll 1
         for (int sub = 0; sub < SUB; sub++) {
             const int i = (int)(((it & 255u) * SUB + sub) * 32u + lane);
             unsigned n1 = 0;
-            if (i < p.B) march_beam<CODED, NOISE, CELLS>(p, a, i, xy, yt.x, yt.y, v, n1);
+            if (i < p.B) march_beam<CODED, NOISE, CELLS>(p, a, i, xy, yt.x, yt.y, v, lo, n1);
             nlook = (SUB == 1) ? n1 : max(nlook, n1);
             if (COUNT) looks += n1;
         }

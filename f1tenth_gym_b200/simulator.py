@@ -57,7 +57,32 @@ class DeviceMap(object):
                              host_map.orig_y, host_map.orig_c, host_map.orig_s, eps, max_range, theta_dis,
                              host_map.fast_path, host_map.dt_oob, nat.ptr(self.dt), nat.ptr(self.dt_cells),
                              nat.ptr(self.dt_codes), nat.ptr(self.dt_lut), nat.ptr(self.sines), nat.ptr(self.cosines),
-                             nat.ptr(self.sincos))
+                             nat.ptr(self.sincos), 1)
+
+    @classmethod
+    def stack(cls, maps):
+        """Multi-map batch: several DeviceMaps that share size, resolution and origin are
+        stacked into one [L][H][W] table; Simulator.set_device_map(stacked, env_map_ids) picks one per env."""
+        m0 = maps[0]
+        for m in maps[1:]:
+            h, h0 = m.host, m0.host
+            if (h.height, h.width, h.resolution, h.orig_x, h.orig_y, h.orig_c, h.orig_s) != \
+               (h0.height, h0.width, h0.resolution, h0.orig_x, h0.orig_y, h0.orig_c, h0.orig_s):
+                raise ValueError('stacked maps must share size, resolution and origin')
+        out = cls.__new__(cls)
+        out.__dict__.update(m0.__dict__)
+        out.layers = list(maps)
+        out.dt = torch.stack([m.dt for m in maps]).contiguous()
+        out.dt_cells = torch.stack([m.dt_cells for m in maps]).contiguous() if m0.dt_cells is not None else None
+        out.dt_codes = out.dt_lut = None
+        c = nat.F110Map.from_buffer_copy(m0.c)
+        c.dt = nat.ptr(out.dt)
+        c.dt_cells = nat.ptr(out.dt_cells)
+        c.dt_codes = None
+        c.dt_lut = None
+        c.num_layers = len(maps)
+        out.c = c
+        return out
 
     @classmethod
     def from_yaml(cls, map_path, map_ext, device, edt='scipy', **kw):
@@ -162,14 +187,14 @@ class Simulator(object):
         self._map_struct = empty_map_struct()
         self._actions_dev = torch.zeros((NA, 2), **f64)
         self.c = nat.F110Sim(
-            N, A, integ, ego_idx, time_step, lidar_dist, 0.005, float(params['length']), float(params['width']),
+            N, A, integ, ego_idx, 0, time_step, lidar_dist, 0.005, float(params['length']), float(params['width']),
             nat.ptr(self.params_dev), nat.ptr(self.state), nat.ptr(self.steer_buf), nat.ptr(self.steer_cnt),
             nat.ptr(self.scan_pose), nat.ptr(self.agent_poses), nat.ptr(self.scans), nat.ptr(self.wall_flag),
             nat.ptr(self.collisions), nat.ptr(self.collision_idx), nat.ptr(self.current_time),
             nat.ptr(self.lap_times), nat.ptr(self.lap_counts), nat.ptr(self.toggle_list),
             nat.ptr(self.near_starts), nat.ptr(self.start_xs), nat.ptr(self.start_ys),
             nat.ptr(self.start_thetas), nat.ptr(self.start_rot), nat.ptr(self.done),
-            nat.ptr(self.checkpoint_done), nat.ptr(self.env_arrivals), nat.ptr(self.lookup_counter), nat.ptr(self.tick_counter),
+            nat.ptr(self.checkpoint_done), nat.ptr(self.env_arrivals), None, nat.ptr(self.lookup_counter), nat.ptr(self.tick_counter),
             nat.ptr(self.march_cost), nat.ptr(self.march_order), nat.ptr(self.march_count), self.march_ipa,
             float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
         self._graph = None
@@ -180,20 +205,54 @@ class Simulator(object):
         exact distance transform on the GPU instead of scipy on the host)."""
         self.set_device_map(DeviceMap.from_yaml(map_path, map_ext, self.device, edt=edt))
 
-    def set_device_map(self, device_map):
+    def set_device_map(self, device_map, env_map_ids=None):
+        """env_map_ids (N,) ints: which layer of a DeviceMap.stack() each env uses (multi-map batches)."""
         self.map = device_map
         self._map_struct = device_map.c
         self._graph = None
-
-    def update_params(self, params, agent_idx=-1):
-        """base_classes.py:514-534.  agent_idx < 0: every agent slot; else that slot in every env."""
-        pv = torch.from_numpy(hostmaps.params_vector(params)).to(self.device)
-        if agent_idx < 0:
-            self.params_dev[:] = pv
-        elif 0 <= agent_idx < self.num_agents:
-            self.params_dev[agent_idx] = pv
+        layers = getattr(device_map.c, 'num_layers', 1)
+        if layers > 1:
+            ids = torch.zeros((self.num_envs,), dtype=torch.int32) if env_map_ids is None else \
+                torch.as_tensor(env_map_ids, dtype=torch.int32)
+            if ids.numel() != self.num_envs or int(ids.min()) < 0 or int(ids.max()) >= layers:
+                raise ValueError('env_map_ids must hold num_envs layer indices in [0, %d)' % layers)
+            self.env_layer = ids.to(self.device).contiguous()
+            self.c.env_layer = nat.ptr(self.env_layer)
         else:
+            self.env_layer = None
+            self.c.env_layer = None
+
+    def update_params(self, params, agent_idx=-1, env_mask=None):
+        """base_classes.py:514-534.  agent_idx < 0: every agent slot; else that slot (in every env).
+        Batch extension: env_mask (N,) bool restricts the update to those envs — the parameter table then
+        becomes per env ([N*A][18], dynamics randomisation); `params` may also be a (N, 18) / (N, A, 18) tensor
+        of per-env parameter vectors (key order maps.PARAM_KEYS)."""
+        if not (agent_idx < 0 or 0 <= agent_idx < self.num_agents):
             raise IndexError('Index given is out of bounds for list of agents.')
+        N, A = self.num_envs, self.num_agents
+        per_env_values = not isinstance(params, dict)
+        if env_mask is None and not per_env_values and not self.c.params_per_env:
+            pv = torch.from_numpy(hostmaps.params_vector(params)).to(self.device)
+            if agent_idx < 0:
+                self.params_dev[:] = pv
+            else:
+                self.params_dev[agent_idx] = pv
+            return
+        if not self.c.params_per_env:        # expand the shared table once
+            self.params_dev = self.params_dev.unsqueeze(0).repeat(N, 1, 1).contiguous()
+            self.c.params = nat.ptr(self.params_dev)
+            self.c.params_per_env = 1
+            self._graph = None
+        if per_env_values:
+            pv = torch.as_tensor(params, dtype=torch.float64).to(self.device)
+            pv = pv.reshape(N, -1, 18)                        # (N,1,18) broadcasts over agents, or (N,A,18)
+        else:
+            pv = torch.from_numpy(hostmaps.params_vector(params)).to(self.device).reshape(1, 1, 18)
+        m = torch.ones((N,), dtype=torch.bool, device=self.device) if env_mask is None else \
+            torch.as_tensor(env_mask).to(device=self.device, dtype=torch.bool)
+        tgt = self.params_dev if agent_idx < 0 else self.params_dev[:, agent_idx:agent_idx + 1]
+        src = pv if (agent_idx < 0 or pv.shape[1] == 1) else pv[:, agent_idx:agent_idx + 1]
+        tgt[m] = src.expand(N, tgt.shape[1], 18)[m]
 
     def set_noise(self, std_dev, seed=None):
         """Scan noise N(0, std_dev^2) (laser_models.py:429,450-452); 0 disables (parity runs)."""

@@ -57,6 +57,8 @@ typedef struct {
     const double *dt_lut;           /* [256] code -> dt_cells value (bit-exact) */
     const double *sines, *cosines;  /* [theta_dis]  sin/cos(linspace(0, 2pi, theta_dis)) (:379-381) */
     const double *sincos;           /* [theta_dis][2] the same values interleaved (sin, cos), or NULL */
+    int32_t num_layers;             /* 0/1: one map.  L > 1: dt and dt_cells hold L stacked [H][W] tables that share size,
+                                       resolution and origin (multi-map batches); f110_sim.env_layer picks one per env */
 } f110_map;
 
 /* Beam tables RaceCar.__init__ builds once (base_classes.py:122-158) + ScanSimulator2D.__init__ (:360-368). */
@@ -72,9 +74,11 @@ typedef struct {
     int32_t num_envs, num_agents;
     int32_t integrator;             /* 1 = RK4, 2 = Euler (base_classes.py:40-42) */
     int32_t ego_idx;
+    int32_t params_per_env;         /* 0: params is [A][18]; 1: params is [N*A][18] */
     double timestep, lidar_dist, ttc_thresh;   /* 0.01, 0.0, 0.005 (base_classes.py:115) */
     double sim_length, sim_width;   /* Simulator.params['length'/'width'] used by check_collision (:549) */
-    const double *params;           /* [A][F110_NPARAM] per agent slot (update_params, base_classes.py:514-534) */
+    const double *params;           /* [A][F110_NPARAM] per agent slot (update_params, base_classes.py:514-534), or
+                                       [N*A][F110_NPARAM] per env and slot when params_per_env != 0 (dynamics randomisation) */
     double *state;                  /* [F110_NSTATE][N*A] */
     double *steer_buf;              /* [2][N*A]   steering delay FIFO, row 0 = newest (base_classes.py:270-278) */
     int32_t *steer_cnt;             /* [N*A] */
@@ -93,6 +97,7 @@ typedef struct {
     uint8_t *done;                  /* [N] */
     uint8_t *checkpoint_done;       /* [N*A]  info['checkpoint_done'] */
     int32_t *env_arrivals;          /* [N] zero-initialised scratch of f110_tick (per-env arrival counter), or NULL */
+    const int32_t *env_layer;       /* [N] map layer of each env for stacked maps (f110_map.num_layers > 1), or NULL */
     unsigned long long *lookup_counter;   /* optional [1]: total DT lookups (roofline denominator); NULL = off */
     unsigned long long *tick_counter;     /* optional [1]: incremented by every f110_step; keys the noise stream
                                              and the auto-reset draw so that CUDA-graph replays stay distinct */

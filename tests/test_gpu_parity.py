@@ -522,3 +522,91 @@ def test_rollout_other_maps_vs_oracle(f110, dev, name):
             assert np.array_equal(col[e], osims[e].collisions), (t, e)
     assert worst_state < TOL_STATE and worst_scan < TOL_SCAN32, (worst_state, worst_scan)
     assert sim.lookups() == sum(o.nlook for o in osims)
+
+
+def test_per_env_params_vs_oracle(f110, dev, example_map):
+    """update_params with per-env parameter vectors (dynamics randomisation): every env follows the oracle run with
+    that env's own parameters."""
+    import oracle
+    N, A, T = 12, 2, 80
+    rng = np.random.default_rng(21)
+    sim = make_sim(f110, dev, example_map, N, A)
+    base = f110.maps.params_vector(f110.maps.DEFAULT_PARAMS)
+    pv = np.tile(base, (N, 1))
+    pv[:, 0] *= rng.uniform(0.7, 1.1, N)        # mu
+    pv[:, 6] *= rng.uniform(0.8, 1.1, N)        # m
+    pv[:, 3] *= rng.uniform(0.93, 1.07, N)      # lf
+    sim.update_params(pv)                        # per env, all agent slots
+    p_slow = dict(f110.maps.DEFAULT_PARAMS, a_max=5.0)
+    mask = np.zeros(N, bool); mask[::3] = True
+    sim.update_params(p_slow, agent_idx=1, env_mask=mask)
+    omap = oracle.OracleMap(example_map.host.dt, example_map.host.resolution,
+                            (example_map.host.orig_x, example_map.host.orig_y, 0.0))
+    poses = _start_poses(f110, rng, N, A)
+    osims = []
+    for e in range(N):
+        o = oracle.OracleSim(omap, num_agents=A)
+        o.params[:] = pv[e]
+        if mask[e]:
+            o.params[1] = oracle.params_vector(p_slow)
+        o.reset(poses[e])
+        osims.append(o)
+    sim.reset(poses)
+    worst = 0.0
+    for t in range(T):
+        act = np.stack([rng.uniform(-0.4189, 0.4189, (N, A)), rng.uniform(1, 8, (N, A))], axis=2)
+        sim.step(act)
+        st = cpu(sim.state).reshape(7, N, A).transpose(1, 2, 0)
+        for e in range(N):
+            osims[e].step(act[e])
+            worst = max(worst, np.abs(st[e] - osims[e].state).max())
+    assert worst < TOL_STATE, worst
+    with pytest.raises(IndexError):
+        sim.update_params(p_slow, agent_idx=5)
+
+
+def test_multi_map_batch_vs_oracle(f110, dev, example_map):
+    """Stacked maps on one canvas (multi-map batches): each env marches on its own layer, exactly like an oracle
+    Simulator built on that map."""
+    import oracle
+    h = example_map.host
+    flipped = f110.maps.HostMap(np.ascontiguousarray(h.dt[::-1, ::-1]), h.resolution, (h.orig_x, h.orig_y, 0.0))
+    dm2 = f110.DeviceMap(flipped, dev)
+    stacked = f110.DeviceMap.stack([example_map, dm2])
+    N, A, T = 10, 2, 50
+    ids = np.array([0, 1] * (N // 2))
+    rng = np.random.default_rng(17)
+    poses = _start_poses(f110, rng, N, A, gap=5)
+    # mirrored envs start at the mirrored pose (the flipped map is the original rotated by pi about the canvas centre)
+    cx = h.orig_x + 0.5 * h.width * h.resolution
+    cy = h.orig_y + 0.5 * h.height * h.resolution
+    for e in range(N):
+        if ids[e]:
+            poses[e, :, 0] = 2 * cx - poses[e, :, 0]
+            poses[e, :, 1] = 2 * cy - poses[e, :, 1]
+            poses[e, :, 2] = np.mod(poses[e, :, 2] + np.pi, 2 * np.pi)
+    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 3, num_envs=N, device=dev, count_lookups=True)
+    sim.set_device_map(stacked, env_map_ids=ids)
+    sim.reset(poses)
+    omaps = [oracle.OracleMap(h.dt, h.resolution, (h.orig_x, h.orig_y, 0.0)),
+             oracle.OracleMap(flipped.dt, h.resolution, (h.orig_x, h.orig_y, 0.0))]
+    osims = [oracle.OracleSim(omaps[ids[e]], num_agents=A) for e in range(N)]
+    for e in range(N):
+        osims[e].reset(poses[e])
+    worst_state = worst_scan = 0.0
+    for t in range(T):
+        act = np.stack([rng.uniform(-0.4189, 0.4189, (N, A)), rng.uniform(0, 8, (N, A))], axis=2)
+        obs = sim.step(act)
+        st = cpu(sim.state).reshape(7, N, A).transpose(1, 2, 0)
+        sc = cpu(obs['scans']).astype(np.float64)
+        for e in range(N):
+            osims[e].step(act[e])
+            worst_state = max(worst_state, np.abs(st[e] - osims[e].state).max())
+            worst_scan = max(worst_scan, np.abs(sc[e] - osims[e].scans).max())
+            assert np.array_equal(cpu(obs['collisions'])[e], osims[e].collisions)
+    assert worst_state < TOL_STATE and worst_scan < TOL_SCAN32, (worst_state, worst_scan)
+    assert sim.lookups() == sum(o.nlook for o in osims)
+    # the two layers really differ: env 0 and env 1 see different scans
+    assert not torch.equal(obs['scans'][0], obs['scans'][1])
+    with pytest.raises(ValueError):
+        sim.set_device_map(stacked, env_map_ids=np.full(N, 2))

@@ -228,7 +228,7 @@ def run_b200(args):
     pool = make_actions(P)
     abuf = torch.zeros((NA, 2), dtype=torch.float64, device=dev)
     sim.capture_graph(abuf, autoreset_poses=wp, pose_gap=POSE_GAP, autoreset_seed=SEED + rank, env_level=True)
-    launches_per_step = 5      # k_dynamics, k_raymarch, k_finalize, k_env_post_step, k_autoreset
+    launches_per_step = 3      # f110_tick: k_dynamics (+queue build), k_march_persistent, k_tail (finalize + lap logic + auto-reset)
 
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     for t in range(W):

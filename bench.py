@@ -294,14 +294,19 @@ def run_b200(args):
 
     # ---- end to end through the host-buffer API (pipelined: the D2H of tick t overlaps the compute of tick t+1)
     Ke = min(K, 300)
-    host_pool = pool[:min(P, 64)].cpu().pin_memory()
+    # the caller's actions live in host memory; they are written into the pinned action buffer with a plain
+    # single-threaded numpy copy (a torch CPU copy_ of > 32 K elements forks an OpenMP team, which costs
+    # milliseconds on a 128-thread box and was what limited the first end-to-end numbers of the 16384-env workloads)
+    host_pool = pool[:min(P, 64)].cpu().numpy()
     sets = sim.make_host_pipeline(depth=2)
+    for io in sets:
+        io['_actions_np'] = io['actions'].numpy()
 
     def e2e_loop(n):
         for t in range(n):
             io = sets[t % 2]
             sim.wait_host(io)                                      # obs of tick t-2 is on the host: io is reusable
-            io['actions'].copy_(host_pool[t % host_pool.shape[0]])      # the caller's new actions (host -> pinned)
+            np.copyto(io['_actions_np'], host_pool[t % host_pool.shape[0]])   # the caller's new actions (host -> pinned)
             sim.step_host_async(io)
             sim.autoreset(wp, POSE_GAP, SEED + rank)
         for io in sets:
@@ -317,11 +322,12 @@ def run_b200(args):
     e2e_s = reduce_max_scalar(e2e_s, dev)
     # the plain synchronous call, for comparison
     io1 = sim.make_host_io()
+    io1['_actions_np'] = io1['actions'].numpy()
     Ks = min(Ke, 100)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for t in range(Ks):
-        io1['actions'].copy_(host_pool[t % host_pool.shape[0]])
+        np.copyto(io1['_actions_np'], host_pool[t % host_pool.shape[0]])
         sim.step_host(io1)
         sim.autoreset(wp, POSE_GAP, SEED + rank)
     torch.cuda.synchronize(dev)

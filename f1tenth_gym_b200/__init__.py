@@ -7,8 +7,9 @@ names).  Compute happens only in libf110_b200.so (hand-written sm_100a CUDA behi
 """
 from .simulator import Integrator, Simulator, DeviceMap, DeviceBeams   # noqa: F401
 from .env import F110Env                                              # noqa: F401
-from . import kernels, maps                                           # noqa: F401
+from . import kernels, maps, trackgen                                 # noqa: F401
 from .kernels import ScanSimulator2D                                  # noqa: F401
 from .planner import PurePursuitPlanner                               # noqa: F401
 
-__all__ = ['F110Env', 'Simulator', 'Integrator', 'ScanSimulator2D', 'PurePursuitPlanner', 'DeviceMap', 'DeviceBeams', 'kernels', 'maps']
+__all__ = ['F110Env', 'Simulator', 'Integrator', 'ScanSimulator2D', 'PurePursuitPlanner', 'DeviceMap', 'DeviceBeams', 'kernels', 'maps',
+           'trackgen']

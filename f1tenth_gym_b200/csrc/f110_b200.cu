@@ -20,6 +20,7 @@
 #include "march.cuh"
 #include "planner.cuh"
 #include "edt.cuh"
+#include "trackgen.cuh"
 
 namespace f110 {
 
@@ -1113,6 +1114,22 @@ int f110_edt(const uint8_t *occupied, int32_t height, int32_t width, double reso
         CUDA_TRY(cudaFuncSetAttribute(k_edt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_edt_rows<<<height, 256, smem, st>>>(scratch, height, width, resolution, dt_out, k_out);
     LAUNCH_CHECK("k_edt_rows");
+    return F110_OK;
+}
+
+int f110_rasterize_track(const double *segments, int32_t num_segments, double wall_inner, double wall_outer, int32_t height,
+                          int32_t width, uint8_t *occupied, double *dist2_out, void *stream) {
+    if (!segments || !occupied || num_segments <= 0 || height <= 0 || width <= 0 || !(wall_inner >= 0) ||
+        !(wall_outer >= wall_inner))
+        return F110_ERR_INVALID;
+    const size_t smem = (size_t)num_segments * 5 * sizeof(double);
+    if (smem > 200 * 1024) return F110_ERR_INVALID;
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_rasterize_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+    k_rasterize_track<<<grid, block, smem, (cudaStream_t)stream>>>(segments, num_segments, wall_inner * wall_inner,
+                                                                    wall_outer * wall_outer, height, width, occupied, dist2_out);
+    LAUNCH_CHECK("k_rasterize_track");
     return F110_OK;
 }
 

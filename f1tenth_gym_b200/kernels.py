@@ -125,6 +125,13 @@ class ScanSimulator2D(object):
         self.map_resolution = self.map.host.resolution
         return True
 
+    def set_device_map(self, device_map):
+        """A DeviceMap built elsewhere (device EDT, generated track) instead of a yaml + image on disk."""
+        self.map = device_map
+        self.map_height, self.map_width = device_map.host.height, device_map.host.width
+        self.map_resolution = device_map.host.resolution
+        return True
+
     def scan(self, pose, rng=None, std_dev=0.01, out_f64=False, count_lookups=False):
         if self.map_height is None:
             raise ValueError('Map is not set for scan simulator.')

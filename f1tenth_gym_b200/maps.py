@@ -51,6 +51,20 @@ class HostMap(object):
         m, e = math.frexp(self.resolution)
         self.fast_path = int(m == 0.5 and self.orig_c == 1.0 and self.orig_s == 0.0)
 
+    @classmethod
+    def meta(cls, height, width, resolution, origin, dt_oob):
+        """Metadata only, for a map whose table exists on the device alone (`DeviceMap.from_device_dt`)."""
+        self = cls.__new__(cls)
+        self.dt = None
+        self.height, self.width = int(height), int(width)
+        self.resolution = float(resolution)
+        self.orig_x, self.orig_y = float(origin[0]), float(origin[1])
+        self.orig_s, self.orig_c = float(np.sin(origin[2])), float(np.cos(origin[2]))
+        self.dt_oob = float(dt_oob)
+        m, e = math.frexp(self.resolution)
+        self.fast_path = int(m == 0.5 and self.orig_c == 1.0 and self.orig_s == 0.0)
+        return self
+
 
 def code_table(values, ncodes=255):
     """Lossless byte coding of a DT grid: code = rank of the cell value among the `ncodes` smallest distinct

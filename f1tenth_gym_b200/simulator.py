@@ -36,20 +36,25 @@ def _stream_ptr(device):
 class DeviceMap(object):
     """ScanSimulator2D state (laser_models.py:348-427) resident in HBM: fp64 DT grid + angle LUTs."""
 
-    def __init__(self, host_map, device, theta_dis=2000, eps=0.0001, max_range=30.0):
+    def __init__(self, host_map, device, theta_dis=2000, eps=0.0001, max_range=30.0, _device_dt=None):
         self.host = host_map
         self.device = device
         self.theta_dis = theta_dis
         sines, cosines = hostmaps.angle_lut(theta_dis)
-        self.dt = torch.from_numpy(host_map.dt).to(device)
         # cell-unit copy for the fast path (res = 2^-k: the division is an exact exponent shift)
         self.dt_cells = self.dt_codes = self.dt_lut = None
-        if host_map.fast_path:
-            cells = host_map.dt / host_map.resolution
-            codes, lut = hostmaps.code_table(cells)
-            self.dt_cells = torch.from_numpy(cells).to(device)
-            self.dt_codes = torch.from_numpy(codes).to(device)
-            self.dt_lut = torch.from_numpy(lut).to(device)
+        if _device_dt is not None:
+            self.dt = _device_dt
+            if host_map.fast_path:
+                self.dt_cells = self.dt / host_map.resolution     # IEEE fp64 division on the device, exact here
+        else:
+            self.dt = torch.from_numpy(host_map.dt).to(device)
+            if host_map.fast_path:
+                cells = host_map.dt / host_map.resolution
+                codes, lut = hostmaps.code_table(cells)
+                self.dt_cells = torch.from_numpy(cells).to(device)
+                self.dt_codes = torch.from_numpy(codes).to(device)
+                self.dt_lut = torch.from_numpy(lut).to(device)
         self.sines = torch.from_numpy(sines).to(device)
         self.cosines = torch.from_numpy(cosines).to(device)
         self.sincos = torch.from_numpy(np.ascontiguousarray(np.stack([sines, cosines], axis=1))).to(device)
@@ -83,6 +88,14 @@ class DeviceMap(object):
         c.num_layers = len(maps)
         out.c = c
         return out
+
+    @classmethod
+    def from_device_dt(cls, dt, resolution, origin, **kw):
+        """A map whose fp64 distance table [H][W] (metres) already lives on the device (e.g. rasterised track +
+        f110_edt): nothing but the out-of-bounds scalar dt[-1,-1] crosses PCIe."""
+        dt = dt.contiguous()
+        meta = hostmaps.HostMap.meta(dt.shape[0], dt.shape[1], resolution, origin, float(dt[-1, -1].item()))
+        return cls(meta, dt.device, _device_dt=dt, **kw)
 
     @classmethod
     def from_yaml(cls, map_path, map_ext, device, edt='scipy', **kw):

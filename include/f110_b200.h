@@ -223,6 +223,15 @@ int f110_pure_pursuit(const double *wx, const double *wy, const double *wv, int3
 int f110_edt(const uint8_t *occupied, int32_t height, int32_t width, double resolution, int32_t *scratch, double *dt_out,
              int64_t *k_out, void *stream);
 
+/* Walls of a generated track (reference unittest/random_trackgen.py:156-165 shapely buffer(+-WIDTH) of the closed
+ * centerline, :167-178 the two offset curves drawn 3 pt wide): segments [num_segments][5] (device) = ax, ay, bx-ax,
+ * by-ay, 1/|b-a|^2 of the closed centerline in PIXEL units (pixel (r, c) has its centre at (c+0.5, r+0.5), row 0 =
+ * bottom of the map like the flipped image of laser_models.py:399); occupied [H][W] u8 = 1 where the pixel centre's
+ * distance d to the centerline satisfies wall_inner <= d <= wall_outer (the input f110_edt takes); dist2_out
+ * (optional) [H][W] f64 = d^2 in pixels^2 (d < wall_inner = on the track). */
+int f110_rasterize_track(const double *segments, int32_t num_segments, double wall_inner, double wall_outer, int32_t height,
+                          int32_t width, uint8_t *occupied, double *dist2_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -812,6 +812,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             MarchQueue mq;
             mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
+            { static int cs = -1; if (cs < 0) { const char *e = getenv("F110_MARCH_CHUNK"); cs = e ? atoi(e) : 3; if (cs < 0 || cs > 6) cs = 3; } mq.chunk_shift = (unsigned)cs; }
             const unsigned blocks = (unsigned)num_sms() * 4u;
             if (!cell_units) launch_persistent<512, 1, false>(k, mq, blocks, coded, noise, count, st);
             else if (item_sub == 2) launch_persistent<512, 2, true>(k, mq, blocks, coded, noise, count, st);

@@ -90,6 +90,7 @@ struct MarchQueue {
     const unsigned *__restrict__ count;     // [3]
     unsigned items;                         // M * ipa
     unsigned ipa;                           // 32-beam slices per agent (<= 256)
+    unsigned chunk_shift;                   // a block is dealt 2^chunk_shift consecutive queue entries at a time
 };
 
 // One beam: LUT heading, sphere tracing in cell units, optional noise, iTTC predicate, fp32 range out.
@@ -229,7 +230,12 @@ __global__ void __launch_bounds__(PT, 4) k_march_persistent(const MarchK p, cons
         unsigned k = 0;
         if (lane == 0) k = atomicAdd(&s_next, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
-        const unsigned q = k * gridDim.x + blockIdx.x;      // items < 2^32 / 4 (host-checked): no overflow
+        // items < 2^32 / 4 (host-checked): no overflow.  Consecutive entries of a class list are neighbouring
+        // slices of one agent, so dealing them in runs of 8 lets the warps of a block share L1 lines (march 80.5 ->
+        // 77.2 us at cfg2; runs of 4 / 16: 80.6 / 79.5 us; also giving the co-resident blocks of an SM neighbouring
+        // runs concentrates the heavy items on few SMs: 86.7 us).
+        const unsigned q = ((((k >> mq.chunk_shift) * gridDim.x + blockIdx.x) << mq.chunk_shift)) +
+                           (k & ((1u << mq.chunk_shift) - 1u));
         if (q >= total) break;
         unsigned long long t0 = 0;
         if (TRACE) t0 = gtime();

@@ -1097,8 +1097,22 @@ int f110_pure_pursuit(const double *wx, const double *wy, const double *wv, int3
     if (!wx || !wy || !wv || num_waypoints < 2 || !pose_x || !pose_y || !pose_theta || M <= 0 || !actions_out)
         return F110_ERR_INVALID;
     k_pure_pursuit<<<((long long)M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        wx, wy, wv, num_waypoints, pose_x, pose_y, pose_theta, M, lookahead_distance, vgain, wheelbase, max_reacquire,
-        actions_out);
+        wx, wy, wv, num_waypoints, nullptr, nullptr, pose_x, pose_y, pose_theta, M, lookahead_distance, vgain, wheelbase,
+        max_reacquire, actions_out);
+    LAUNCH_CHECK("k_pure_pursuit");
+    return F110_OK;
+}
+
+int f110_pure_pursuit_tables(const double *wx, const double *wy, const double *wv, const int32_t *table_start,
+                             int32_t num_tables, const int32_t *pose_table, const double *pose_x, const double *pose_y,
+                             const double *pose_theta, int32_t M, double lookahead_distance, double vgain, double wheelbase,
+                             double max_reacquire, double *actions_out, void *stream) {
+    if (!wx || !wy || !wv || !table_start || num_tables <= 0 || !pose_table || !pose_x || !pose_y || !pose_theta || M <= 0 ||
+        !actions_out)
+        return F110_ERR_INVALID;
+    k_pure_pursuit<<<((long long)M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        wx, wy, wv, 0, table_start, pose_table, pose_x, pose_y, pose_theta, M, lookahead_distance, vgain, wheelbase,
+        max_reacquire, actions_out);
     LAUNCH_CHECK("k_pure_pursuit");
     return F110_OK;
 }

@@ -7,6 +7,7 @@
 // intersected segment (wpts[i2]), the speed is taken from the NEAREST segment's row, `end = next + 1e-6`.
 #pragma once
 #include <math.h>
+#include <stdint.h>
 
 namespace f110 {
 
@@ -26,9 +27,13 @@ __device__ __forceinline__ bool pp_segment_hits(double sx, double sy, double ex,
     return (t1 >= 0.0 && t1 <= 1.0) || (t2 >= 0.0 && t2 <= 1.0);
 }
 
-// actions_out[a] = (steering angle, speed): the layout f110_step consumes
+// actions_out[a] = (steering angle, speed): the layout f110_step consumes.
+// Several waypoint tables (one per track of a multi-map batch) are concatenated in wx/wy/wv: table t occupies
+// [table_start[t], table_start[t+1]) and pose a follows table pose_table[a]; table_start == NULL: one table of n rows.
 __global__ void __launch_bounds__(128) k_pure_pursuit(const double *__restrict__ wx, const double *__restrict__ wy,
                                                       const double *__restrict__ wv, int n,
+                                                      const int32_t *__restrict__ table_start,
+                                                      const int32_t *__restrict__ pose_table,
                                                       const double *__restrict__ pose_x, const double *__restrict__ pose_y,
                                                       const double *__restrict__ pose_theta, int M, double lookahead,
                                                       double vgain, double wheelbase, double max_reacquire,
@@ -36,6 +41,12 @@ __global__ void __launch_bounds__(128) k_pure_pursuit(const double *__restrict__
     const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (a >= M) return;
+    if (table_start) {
+        const int t = pose_table[a];
+        const int off = table_start[t];
+        n = table_start[t + 1] - off;
+        wx += off; wy += off; wv += off;
+    }
     const double px = pose_x[a], py = pose_y[a], th = pose_theta[a];
     // nearest_point_on_trajectory: np.argmin = first minimum
     double bd = INFINITY, bt = 0.0;

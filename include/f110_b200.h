@@ -216,6 +216,15 @@ int f110_pure_pursuit(const double *wx, const double *wy, const double *wv, int3
                       const double *pose_y, const double *pose_theta, int32_t M, double lookahead_distance, double vgain,
                       double wheelbase, double max_reacquire, double *actions_out, void *stream);
 
+/* The same policy over several waypoint tables (one per track of a multi-map batch; batch extension, no reference
+ * counterpart): the tables are concatenated in wx/wy/wv, table t occupies rows [table_start[t], table_start[t+1])
+ * (table_start [num_tables+1] i32, device, every table >= 2 rows) and pose a follows table pose_table[a]
+ * (i32 [M], device, values in [0, num_tables) -- not range-checked on the device). */
+int f110_pure_pursuit_tables(const double *wx, const double *wy, const double *wv, const int32_t *table_start,
+                             int32_t num_tables, const int32_t *pose_table, const double *pose_x, const double *pose_y,
+                             const double *pose_theta, int32_t M, double lookahead_distance, double vgain, double wheelbase,
+                             double max_reacquire, double *actions_out, void *stream);
+
 /* Exact Euclidean distance transform on the device (load-time; reference laser_models.py:40-53 get_dt =
  * resolution * scipy.ndimage.distance_transform_edt(bitmap)): occupied [H][W] u8 (1 where the thresholded image
  * is 0), scratch [H][W] i32, dt_out [H][W] f64 = resolution * sqrt(k) with k the exact squared cell distance

@@ -188,3 +188,38 @@ def test_closed_loop_two_laps_on_generated_track():
     assert np.all(sim.lap_counts.cpu().numpy() >= 2.0)
     laps = sim.lap_times.cpu().numpy()
     assert np.all(np.abs(laps - 2 * lap_len / 5.0) < 0.15 * 2 * lap_len / 5.0), laps
+
+
+@pytest.mark.gpu
+def test_closed_loop_on_stacked_tracks_with_per_env_waypoint_tables():
+    """Domain randomisation end to end on the device: three generated tracks in one multi-map batch, every env driven
+    by pure pursuit on the centerline of ITS track (f110_pure_pursuit_tables), two clean laps everywhere."""
+    import torch
+    import f1tenth_gym_b200 as f110
+    dev = torch.device('cuda:0')
+    tracks = tg.random_tracks(11, 3)
+    stacked, _ = tg.device_maps(tracks, dev)
+    N = 6
+    ids = np.arange(N) % 3
+    starts = np.stack([tracks[ids[e]].start_pose(40 * e)[None] for e in range(N)])
+    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, 1, 3, num_envs=N, device=dev)
+    sim.set_device_map(stacked, env_map_ids=ids)
+    sim.env_reset(starts)
+    pl = f110.PurePursuitPlanner(device=dev, waypoints=[t.raceline(speed=5.0) for t in tracks], xind=0, yind=1, vind=2)
+    obs = sim.observations()
+    # the multi-table kernel is the single-table kernel on each subset
+    multi = pl.plan_actions(obs, 1.2, 1.0, table_ids=ids).clone()
+    for k, t in enumerate(tracks):
+        single = f110.PurePursuitPlanner(device=dev, waypoints=t.raceline(speed=5.0), xind=0, yind=1, vind=2)
+        assert torch.equal(single.plan_actions(obs, 1.2, 1.0)[ids == k], multi[ids == k])
+    with pytest.raises(ValueError):
+        pl.plan_actions(obs, 1.2, 1.0)
+    longest = max(np.linalg.norm(np.roll(t.waypoints, -1, 0) - t.waypoints, axis=1).sum() for t in tracks)
+    tid = torch.as_tensor(ids, device=dev)
+    for k in range(int(2.6 * longest / 5.0 / 0.01)):
+        obs = sim.tick(pl.plan_actions(obs, 1.2, 1.0, table_ids=tid))
+        if k % 200 == 199 and bool(sim.done.all()):
+            break
+    assert bool(sim.done.all()), sim.lap_counts.cpu().numpy()
+    assert float(sim.collisions.sum()) == 0.0
+    assert np.all(sim.lap_counts.cpu().numpy() >= 2.0)

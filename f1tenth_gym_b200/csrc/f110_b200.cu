@@ -73,34 +73,69 @@ static BeamView make_view(const f110_beams *b) {
 // Work queue of the persistent march kernel (march.cuh): sort the 32-beam items into [very heavy | heavy |
 // light] by the maximum lookup count they recorded in the previous tick.  One thread per item; runs as the
 // extra blocks of k_dynamics (it only reads march_cost, which the reset kernels mark as unknown).
-__device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned w, unsigned items) {
+#define F110_ORDER_ITEMS_PER_THREAD 8
+__device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned first_block, unsigned items) {
+    // (1) these blocks run at the occupancy of the 122-register dynamics path (16 warps/SM), so each thread classifies
+    // eight items with all its loads in flight together; (2) the three class counters are single addresses: one
+    // atomic per warp and class serialises in L2 (52 k same-address atomics at cfg3 = the whole 60 us of the kernel),
+    // so slots are handed out from shared-memory counters and the block claims its ranges with three global atomics.
+    __shared__ unsigned s_cnt[3], s_base[3];
     const unsigned lane = threadIdx.x & 31u;
-    int cls = -1;
-    unsigned packed = 0;
-    if (w < items) {
-        const unsigned ipa = (unsigned)s.march_ipa;
-        const unsigned a = w / ipa, j = w - a * ipa;
-        packed = (a << 8) | j;
-        const unsigned c = s.march_cost[packed];
-        unsigned m = c;
-        if (c != F110_Q_UNKNOWN) {
-            if (j > 0) { const unsigned cl = s.march_cost[packed - 1]; if (cl != F110_Q_UNKNOWN) m = max(m, cl); }
-            if (j + 1 < ipa) { const unsigned cr = s.march_cost[packed + 1]; if (cr != F110_Q_UNKNOWN) m = max(m, cr); }
-        }
-        cls = (c == F110_Q_UNKNOWN || c >= F110_Q_VERY_HEAVY) ? 0 : (m >= F110_Q_HEAVY) ? 1 : 2;
-    }
+    const unsigned warp = (((blockIdx.x - first_block) * blockDim.x + threadIdx.x) >> 5);
+    const unsigned ipa = (unsigned)s.march_ipa;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+    int cls[F110_ORDER_ITEMS_PER_THREAD];
+    unsigned packed[F110_ORDER_ITEMS_PER_THREAD], slot[F110_ORDER_ITEMS_PER_THREAD];
+    {
+        unsigned c[F110_ORDER_ITEMS_PER_THREAD], cl[F110_ORDER_ITEMS_PER_THREAD], cr[F110_ORDER_ITEMS_PER_THREAD];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const unsigned msk = __ballot_sync(0xffffffffu, cls == k);
-        if (msk) {
-            unsigned base = 0;
-            const int leader = __ffs(msk) - 1;
-            if ((int)lane == leader) base = atomicAdd(s.march_count + k, (unsigned)__popc(msk));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (cls == k) {
-                const unsigned slot = base + (unsigned)__popc(msk & ((1u << lane) - 1u));
-                if (slot < items) s.march_order[(size_t)k * items + slot] = packed;
+        for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
+            const unsigned w = (warp * F110_ORDER_ITEMS_PER_THREAD + (unsigned)k) * 32u + lane;
+            cls[k] = -1; packed[k] = 0; slot[k] = 0; c[k] = cl[k] = cr[k] = F110_Q_UNKNOWN;
+            if (w < items) {
+                const unsigned a = w / ipa, j = w - a * ipa;
+                packed[k] = (a << 8) | j;
+                c[k] = s.march_cost[packed[k]];
+                if (j > 0) cl[k] = s.march_cost[packed[k] - 1];
+                if (j + 1 < ipa) cr[k] = s.march_cost[packed[k] + 1];
+                cls[k] = 0;
             }
+        }
+#pragma unroll
+        for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
+            if (cls[k] == 0) {
+                unsigned m = c[k];
+                if (c[k] != F110_Q_UNKNOWN) {
+                    if (cl[k] != F110_Q_UNKNOWN) m = max(m, cl[k]);
+                    if (cr[k] != F110_Q_UNKNOWN) m = max(m, cr[k]);
+                }
+                cls[k] = (c[k] == F110_Q_UNKNOWN || c[k] >= F110_Q_VERY_HEAVY) ? 0 : (m >= F110_Q_HEAVY) ? 1 : 2;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const unsigned msk = __ballot_sync(0xffffffffu, cls[k] == q);
+            if (msk) {
+                unsigned base = 0;
+                const int leader = __ffs(msk) - 1;
+                if ((int)lane == leader) base = atomicAdd(&s_cnt[q], (unsigned)__popc(msk));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (cls[k] == q) slot[k] = base + (unsigned)__popc(msk & ((1u << lane) - 1u));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(s.march_count + threadIdx.x, s_cnt[threadIdx.x]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
+        if (cls[k] >= 0) {
+            const unsigned at = s_base[cls[k]] + slot[k];
+            if (at < items) s.march_order[(size_t)cls[k] * items + at] = packed[k];
         }
     }
 }
@@ -120,8 +155,7 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
                                                   double theta_dis_f, int dyn_blocks, FirstLookup fl) {
     const int NA = s.num_envs * s.num_agents;
     if ((int)blockIdx.x >= dyn_blocks) {     // extra blocks: build the march work queue (block-uniform branch)
-        build_march_order(s, (blockIdx.x - (unsigned)dyn_blocks) * blockDim.x + threadIdx.x,
-                          (unsigned)NA * (unsigned)s.march_ipa);
+        build_march_order(s, (unsigned)dyn_blocks, (unsigned)NA * (unsigned)s.march_ipa);
         return;
     }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -757,7 +791,8 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                         (unsigned long long)NA < (1ull << 22) &&
                         map->orig_c == 1.0 && map->orig_s == 0.0 && map->sincos && beams->cos_side && variant != 13;
     const int dyn_blocks = (NA + 127) / 128;
-    const int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 127) / 128) : 0;
+    const int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 128 * F110_ORDER_ITEMS_PER_THREAD - 1) /
+                                         (128 * F110_ORDER_ITEMS_PER_THREAD)) : 0;
     // the lean march kernels need an unrotated map origin and the interleaved tables; cell units additionally a
     // power-of-two resolution (fast_path) and the cell-unit table
     const bool cell_march = map->orig_c == 1.0 && map->orig_s == 0.0 && map->sincos && beams->cos_side &&

@@ -526,27 +526,27 @@ __global__ void k_autoreset(f110_sim s, AutoResetArgs ar) {
 
 // f110_tick: warp per agent; the warp that finishes an env last (per-env arrival counter) also runs the F110Env
 // lap logic and the auto-reset for that env: k_finalize + k_env_post_step + k_autoreset in one launch
-__global__ void __launch_bounds__(128, 8) k_tail(f110_sim s, BeamView bv, int env_level, AutoResetArgs ar,
-                                                 double max_scan_range) {
-    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(1024, 1) k_tail(f110_sim s, BeamView bv, int env_level, AutoResetArgs ar,
+                                                   double max_scan_range, int envs_per_block) {
+    // a block owns whole envs (blockDim = 32 * A * envs_per_block, A <= 32): the env-level step only needs what the
+    // warps of its own block wrote, so a block barrier orders it -- no device-scope fence, no arrival atomics.  (The
+    // first version had every warp execute __threadfence() + atomicAdd on a per-env counter; the fence's L1
+    // invalidation (CCTL.IVALL) kept evicting the beam tables and poses of the other warps on the SM: 19 % of the
+    // kernel's stall samples sat on the fences and 8 % on the scan-angle loads behind them.)
+    const int A = s.num_agents;
     const int lane = threadIdx.x & 31;
-    if (a >= s.num_envs * s.num_agents) return;
-    finalize_agent(s, bv, a, lane, max_scan_range);
-    __syncwarp();
-    if (lane == 0) {
-        const int env = a / s.num_agents;
-        bool last = true;
-        if (s.num_agents > 1) {
-            __threadfence();                                     // publish this agent's state / collisions
-            last = atomicAdd(s.env_arrivals + env, 1) == s.num_agents - 1;
-            if (last) { s.env_arrivals[env] = 0; __threadfence(); }
-        }
-        if (last) {
+    const int env0 = blockIdx.x * envs_per_block;
+    const int a = env0 * A + (int)(threadIdx.x >> 5);
+    if (a < s.num_envs * A) finalize_agent(s, bv, a, lane, max_scan_range);
+    __syncthreads();
+    if ((int)threadIdx.x < envs_per_block) {
+        const int env = env0 + (int)threadIdx.x;
+        if (env < s.num_envs) {
             if (env_level) env_post_step_one(s, env);
             if (ar.start_poses) autoreset_one(s, env, ar);
         }
-        if (a == 0) end_of_tick_housekeeping(s);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) end_of_tick_housekeeping(s);
 }
 
 // ------------------------------------------------------------------------------------ standalone kernels
@@ -882,13 +882,16 @@ marched:
 
     // largest value a scan entry can hold: the max_range clamp plus 8 sigma of the optional noise
     const double max_scan = map->max_range + 8.0 * (sim->noise_std > 0.0 ? sim->noise_std : 0.0) + 1e-3;
-    if (tail && tail->fused && (sim->num_agents == 1 || sim->env_arrivals)) {
-        k_tail<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv, tail->env_level, tail->ar, max_scan);
+    if (tail && tail->fused && sim->num_agents <= 32) {
+        // whole envs per block, ~4 warps per block: A = 1 -> 4 envs, A = 2 -> 2 envs, A >= 4 -> 1 env
+        const int epb = sim->num_agents >= 4 ? 1 : 4 / sim->num_agents;
+        const int threads = 32 * sim->num_agents * epb;
+        k_tail<<<(sim->num_envs + epb - 1) / epb, threads, 0, st>>>(*sim, bv, tail->env_level, tail->ar, max_scan, epb);
         LAUNCH_CHECK("k_tail");
     } else {
         k_finalize<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv, max_scan);
         LAUNCH_CHECK("k_finalize");
-        if (tail && tail->fused) {     // no arrival counters bound: same semantics with separate launches
+        if (tail && tail->fused) {     // more than 32 agents per env: same semantics with separate launches
             if (tail->env_level) { k_env_post_step<<<(sim->num_envs + 127) / 128, 128, 0, st>>>(*sim); LAUNCH_CHECK("k_env_post_step"); }
             if (tail->ar.start_poses) { k_autoreset<<<(sim->num_envs + 127) / 128, 128, 0, st>>>(*sim, tail->ar); LAUNCH_CHECK("k_autoreset"); }
         }

@@ -96,7 +96,7 @@ typedef struct {
     double *start_rot;              /* [N][4] */
     uint8_t *done;                  /* [N] */
     uint8_t *checkpoint_done;       /* [N*A]  info['checkpoint_done'] */
-    int32_t *env_arrivals;          /* [N] zero-initialised scratch of f110_tick (per-env arrival counter), or NULL */
+    int32_t *env_arrivals;          /* reserved (ABI v1 used it as a per-env arrival counter of f110_tick); may be NULL */
     const int32_t *env_layer;       /* [N] map layer of each env for stacked maps (f110_map.num_layers > 1), or NULL */
     unsigned long long *lookup_counter;   /* optional [1]: total DT lookups (roofline denominator); NULL = off */
     unsigned long long *tick_counter;     /* optional [1]: incremented by every f110_step; keys the noise stream

@@ -964,6 +964,7 @@ int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_s
     if ((rc = check_sim(sim))) return rc;
     if (!start_poses || num_start <= 0) return F110_ERR_INVALID;
     if (sim->ego_idx < 0 || sim->ego_idx >= sim->num_agents) return F110_ERR_AGENT_INDEX;
+    if (sim->num_agents > 32) return F110_ERR_INVALID;      // the device-side auto-reset stages at most 32 start poses per env
     AutoResetArgs ar;
     ar.start_poses = start_poses; ar.num_start = num_start; ar.pose_gap = pose_gap; ar.seed = seed; ar.tick_host = tick;
     k_autoreset<<<(sim->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*sim, ar);
@@ -977,7 +978,8 @@ int f110_tick(const f110_sim *sim, const f110_map *map, const f110_beams *beams,
     int rc;
     if ((rc = check_sim(sim))) return rc;
     if (env_level && (rc = check_env_arrays(sim))) return rc;
-    if (start_poses && (num_start <= 0 || sim->ego_idx < 0 || sim->ego_idx >= sim->num_agents)) return F110_ERR_INVALID;
+    if (start_poses && (num_start <= 0 || sim->ego_idx < 0 || sim->ego_idx >= sim->num_agents || sim->num_agents > 32))
+        return F110_ERR_INVALID;
     TailOpts t;
     t.fused = true; t.env_level = env_level;
     t.ar.start_poses = start_poses; t.ar.num_start = num_start; t.ar.pose_gap = pose_gap; t.ar.seed = seed; t.ar.tick_host = 0;

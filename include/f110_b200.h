@@ -143,7 +143,8 @@ int f110_env_post_step(const f110_sim *sim, void *stream);
 
 /* Benchmark/RL convenience (no reference equivalent; SURVEY.md 8d policy): every env whose ego has
  * collisions != 0 is reset (Simulator.reset + env counters) to start_poses[k], k drawn from a
- * counter-based hash of (seed, tick, env); agent i takes start_poses[(k - pose_gap*i) mod K]. */
+ * counter-based hash of (seed, tick, env); agent i takes start_poses[(k - pose_gap*i) mod K].
+ * At most 32 agents per env (F110_ERR_INVALID otherwise; stepping itself has no such limit). */
 int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_start, int32_t pose_gap,
                    uint64_t seed, uint64_t tick, void *stream);
 

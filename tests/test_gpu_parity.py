@@ -263,6 +263,44 @@ def test_update_params_and_errors(f110, dev, example_map):
     assert np.abs(st - osim.state).max() < TOL_STATE
 
 
+def test_many_agents_per_env_vs_oracle(f110, dev, example_map):
+    """34 agents in one env (the reference has no limit): lane-strided GJK / opponent loops, the > 32-agent tail path
+    of f110_tick (separate launches), and the documented auto-reset limit."""
+    import oracle
+    N, A, T = 2, 34, 12
+    wp = f110.maps.load_waypoints()
+    rng = np.random.default_rng(21)
+    poses = np.zeros((N, A, 3))
+    for e in range(N):
+        k = int(rng.integers(0, wp.shape[0]))
+        for i in range(A):
+            poses[e, i] = wp[(k - 6 * i) % wp.shape[0]]          # a 1.2 m-spaced train: neighbours occlude each other
+    sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 3, num_envs=N, device=dev)
+    sim.set_device_map(example_map)
+    sim.env_reset(poses)
+    h = example_map.host
+    omap = oracle.OracleMap(h.dt, h.resolution, (h.orig_x, h.orig_y, 0.0))
+    osims = [oracle.OracleSim(omap, num_agents=A) for _ in range(N)]
+    for e in range(N):
+        osims[e].reset(poses[e])
+    worst_state = worst_scan = 0.0
+    for t in range(T):
+        act = np.stack([rng.uniform(-0.3, 0.3, (N, A)), rng.uniform(0, 6, (N, A))], axis=2)
+        obs = sim.tick(act) if t % 2 else sim.step(act)
+        st = cpu(sim.state).reshape(7, N, A).transpose(1, 2, 0)
+        sc = cpu(obs['scans']).astype(np.float64)
+        for e in range(N):
+            osims[e].step(act[e])
+            worst_state = max(worst_state, np.abs(st[e] - osims[e].state).max())
+            worst_scan = max(worst_scan, np.abs(sc[e] - osims[e].scans).max())
+            assert np.array_equal(cpu(obs['collisions'])[e], osims[e].collisions)
+            assert np.array_equal(cpu(sim.collision_idx).reshape(N, A)[e], osims[e].collision_idx)
+    assert worst_state < TOL_STATE and worst_scan < TOL_SCAN32, (worst_state, worst_scan)
+    assert abs(float(sim.current_time[0]) - 0.01 * (T // 2)) < 1e-12          # env time advanced by the tick() calls only
+    with pytest.raises(f110._native.F110Error):                              # documented limit of the device auto-reset
+        sim.autoreset(torch.from_numpy(wp).to(dev))
+
+
 # ----------------------------------------------------------------------------- size-independent properties
 def test_full_size_properties(f110, dev, example_map):
     """BASELINE config sizes: determinism, batch-size invariance, physical bounds, map symmetry of

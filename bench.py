@@ -197,9 +197,21 @@ def run_b200(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep stdout to the one JSON line
-        dist.init_process_group('nccl', rank=rank, world_size=world,
-                                device_id=torch.device('cuda', local_rank))
+        # NCCL prints its version banner to stdout while the communicator is created (NCCL_DEBUG=VERSION ignores
+        # NCCL_DEBUG_FILE); stdout must carry exactly one JSON line, so fd 1 points at stderr during the set-up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', rank=rank, world_size=world,
+                                    device_id=torch.device('cuda', local_rank))
+            torch.cuda.set_device(local_rank)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     w = WORKLOADS[args.workload]

@@ -81,6 +81,45 @@ def test_vertices_and_gjk(f110):
     assert cpu(f110.kernels.collision(jp[:, 0], jp[:, 1])).all()       # :306-311
 
 
+def test_reference_fps_floors(f110, dev):
+    """The reference's own speed floors, same loops, same call granularity (one pose / one state / one pair per call,
+    result on the host each time): laser_models.py:534-552 (> 500 scans/s on berlin, noise on),
+    dynamic_models.py:268-279 (> 5000 RHS calls/s), collision_models.py:326-336 (> 500 GJK calls/s)."""
+    import time
+    ss = f110.ScanSimulator2D(1080, 4.7, device=dev)
+    ss.set_map(os.path.join(MAPS, 'berlin.yaml'), '.png')
+    ss.scan(np.array([0.0, 0., 0.]), 12345)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for i in range(2000):
+        scan = ss.scan(np.array([i / 2000, 0., 0.]), 12345).cpu()
+    fps = 2000 / (time.time() - t0)
+    assert fps > 500., fps
+    k = g('kat_reference_tests.npz')
+    t0 = time.time()
+    for i in range(2000):
+        f_st = f110.kernels.vehicle_dynamics_st(k['x_st'][None], k['u'][None], k['pvec']).cpu()
+    calls_per_s = 2000 / (time.time() - t0)                # one launch + one D2H sync per call
+    v1 = np.asarray([[4, 11.], [5, 5], [9, 9], [10, 10]])
+    rng = np.random.default_rng(0)
+    t0 = time.time()
+    for _ in range(1000):
+        a = v1 + rng.normal(size=v1.shape) / 100.
+        b = v1 + rng.normal(size=v1.shape) / 100.
+        hit = f110.kernels.collision(a[None], b[None]).cpu()
+    gjk = 1000 / (time.time() - t0)
+    assert gjk > 500, gjk
+    assert bool(hit[0])
+    # a per-call launch + host sync costs ~20-40 us, so the 5000 calls/s floor of the scalar RHS needs the batch API:
+    X = np.repeat(k['x_st'][None], 4096, axis=0)
+    U = np.repeat(k['u'][None], 4096, axis=0)
+    t0 = time.time()
+    for i in range(50):
+        F = f110.kernels.vehicle_dynamics_st(X, U, k['pvec']).cpu()
+    assert 50 * 4096 / (time.time() - t0) > 5000
+    assert calls_per_s > 1000, calls_per_s
+
+
 def test_ray_cast_and_window(f110, dev):
     k = g('kat_kernels.npz')
     beams = f110.DeviceBeams(1080, 4.7, f110.maps.DEFAULT_PARAMS, dev)

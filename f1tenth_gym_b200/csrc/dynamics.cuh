@@ -47,8 +47,10 @@ __device__ __forceinline__ void vehicle_dynamics_st(const double x[7], double u_
         double v1 = accl_constraints(x[3], u1, p[P_VSWITCH], p[P_AMAX], p[P_VMIN], p[P_VMAX]);
         double tan_d = tan(x[2]);
         double cos_d = cos(x[2]);
-        f[0] = x[3] * cos(x[4]);
-        f[1] = x[3] * sin(x[4]);
+        double s4, c4;
+        sincos(x[4], &s4, &c4);         // one range reduction; same values as sin() / cos() (tests pin the state)
+        f[0] = x[3] * c4;
+        f[1] = x[3] * s4;
         f[2] = v0;
         f[3] = v1;
         f[4] = x[3] / lwb * tan_d;
@@ -56,8 +58,10 @@ __device__ __forceinline__ void vehicle_dynamics_st(const double x[7], double u_
         f[6] = 0.;
     } else {
         double ang = x[6] + x[4];
-        f[0] = x[3] * cos(ang);
-        f[1] = x[3] * sin(ang);
+        double sa, ca;
+        sincos(ang, &sa, &ca);
+        f[0] = x[3] * ca;
+        f[1] = x[3] * sa;
         f[2] = u0;
         f[3] = u1;
         f[4] = x[5];
@@ -76,11 +80,14 @@ __device__ __forceinline__ void pid(double speed, double steer, double current_s
                                     double max_sv, double max_a, double max_v, double min_v, double &accl,
                                     double &sv) {
     double steer_diff = steer - current_steer;
-    sv = (fabs(steer_diff) > 1e-4) ? (steer_diff / fabs(steer_diff)) * max_sv : 0.0;
+    // steer_diff / |steer_diff| is exactly +-1 for a finite non-zero value: no division needed
+    sv = (fabs(steer_diff) > 1e-4) ? copysign(1.0, steer_diff) * max_sv : 0.0;
     double vel_diff = speed - current_speed;
-    double kp;
-    if (current_speed > 0.) kp = (vel_diff > 0) ? 10.0 * max_a / max_v : 10.0 * max_a / (-min_v);
-    else kp = (vel_diff > 0) ? 2.0 * max_a / max_v : 2.0 * max_a / (-min_v);
+    // the four kp cases (:198-213) are (10|2) * max_a / (max_v | -min_v): selecting the operands first gives the
+    // same two roundings with one division and no divergence
+    const double num = ((current_speed > 0.) ? 10.0 : 2.0) * max_a;
+    const double den = (vel_diff > 0) ? max_v : -min_v;
+    const double kp = num / den;
     accl = kp * vel_diff;
 }
 

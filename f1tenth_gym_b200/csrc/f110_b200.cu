@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
     // computation of the finalize kernel reuses them instead of re-evaluating fp64 trig per opponent
     double *ap = s.agent_poses + 5 * (size_t)a;
     ap[0] = st[0]; ap[1] = st[1]; ap[2] = st[4];
-    ap[3] = cos(st[4]); ap[4] = sin(st[4]);
+    sincos(st[4], ap + 4, ap + 3);
     s.wall_flag[a] = 0;
 }
 
@@ -357,7 +357,8 @@ __device__ __forceinline__ void finalize_agent(const f110_sim &s, const BeamView
                 // direction test, so a beam pointing exactly away along an edge line still reports that edge)
                 const double adl = fabs(dl);
                 if (adl > cone && (M_PI - adl) > cone) continue;
-                double v3x = cos(bt + M_PI / 2.), v3y = sin(bt + M_PI / 2.);
+                double v3x, v3y;
+                sincos(bt + M_PI / 2., &v3y, &v3x);
                 double r = INFINITY;
 #pragma unroll
                 for (int e = 0; e < 4; e++) {

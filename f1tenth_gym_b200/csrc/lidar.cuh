@@ -119,7 +119,7 @@ __device__ __forceinline__ double trace_ray(const MapView &m, double x, double y
 // laser_models.py:167-172: first beam's LUT index from the scan pose yaw.
 __device__ __forceinline__ double theta_index0(double yaw, double fov, double theta_dis_f) {
     double ti = theta_dis_f * (yaw - fov / 2.) / (2. * M_PI);
-    ti = fmod(ti, theta_dis_f);
+    if (!(fabs(ti) < theta_dis_f)) ti = fmod(ti, theta_dis_f);      // fmod(x, y) == x for |x| < |y|: the usual case
     while (ti < 0) ti += theta_dis_f;
     return ti;
 }

@@ -1,0 +1,45 @@
+"""bench.py contract (CPU): the reference arm runs here (it times the oracle port on the host cores) and prints one
+JSON line with the agreed keys; the committed round-1 bench line of the CUDA arm carries every key of the contract."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+BASE_KEYS = ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+             'vs_baseline', 'dtype', 'data', 'config', 'e2e')
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '3',
+                          '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in BASE_KEYS:
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['steps'] == 3 and d['warmup'] >= 3          # W >= 3 is enforced
+    assert d['metric'] == json.load(open(os.path.join(ROOT, 'BASELINE.json')))['metric']
+    assert d['config']['workload'] == 'cfg2' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_committed_bench_line_has_every_contract_key():
+    d = json.load(open(os.path.join(ROOT, 'profiles', 'r1', 'bench_cfg2_final.json')))
+    for k in BASE_KEYS + ('clocks', 'gpu_launches', 'roofline', 'cpu_baseline'):
+        assert k in d, k
+    assert d['n_gpus'] == 1 and d['warmup'] >= 3 and d['scaling'] == 'weak' and d['dtype'] == 'f64'
+    assert d['gpu_launches'] == 3 * d['steps']
+    assert set(('sm_mhz', 'sm_max_mhz', 'reasons')) <= set(d['clocks'])
+    assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+    r = d['roofline']
+    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert r['traffic'] is None or r['traffic'] > 0
+    e = d['e2e']
+    assert e['h2d_bytes_per_step'] == 4096 * 2 * 8 and e['d2h_bytes_per_step'] > 4096 * 1080 * 4
+    assert 0 < e['value'] < d['value']                       # host copies inside the timed region
+    c = d['cpu_baseline']
+    assert c['kind'] in ('port', 'reference') and c['cores'] >= 1 and c['value'] > 0 and c['sample']
+    assert abs(d['value'] - d['steps'] * 4096 / (d['ms_per_step'] * d['steps'] * 1e-3)) / d['value'] < 1e-6

@@ -26,7 +26,16 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-METRIC = 'agent-steps/sec (1080-beam scan)'
+def _baseline_metric():
+    """The metric string is BASELINE.json's, verbatim."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'BASELINE.json')) as f:
+            return json.load(f)['metric']
+    except Exception:
+        return 'agent-steps/sec (1080-beam scan) at 1/2/4/8 B200 vs reference numba CPU'
+
+
+METRIC = _baseline_metric()
 UNIT = 'agent-steps/s'
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on

@@ -149,7 +149,8 @@ int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_s
                    uint64_t seed, uint64_t tick, void *stream);
 
 /* One whole tick in three launches: f110_step + (env_level != 0) f110_env_post_step + (start_poses != NULL)
- * f110_autoreset, with the last three fused into one kernel (one warp per env).  Same results as calling
+ * f110_autoreset, with the finalize kernel of the step, the lap logic and the auto-reset fused into one kernel (a
+ * block owns whole envs; with more than 32 agents per env they run as separate launches).  Same results as calling
  * the three entry points in that order.  This is what a training loop / CUDA graph should replay. */
 int f110_tick(const f110_sim *sim, const f110_map *map, const f110_beams *beams, const double *actions,
               int32_t env_level, const double *start_poses, int32_t num_start, int32_t pose_gap, uint64_t seed,

@@ -164,7 +164,13 @@ def cpu_rollout_rate(workload, seconds_target, steps=None, warmup=0, threads=0):
         total += n
         nlook += l
     dt = time.perf_counter() - t0
-    return {'value': total / dt, 'unit': UNIT, 'cores': nthreads, 'host_cores': cores,
+    host = {'os_cpu_count': os.cpu_count(), 'affinity': len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else None}
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            host['cgroup_cpu_max'] = f.read().strip()          # "max 100000" = no quota
+    except Exception:
+        host['cgroup_cpu_max'] = None
+    return {'value': total / dt, 'unit': UNIT, 'cores': nthreads, 'host_cores': cores, 'host': host,
             'sample': '%d of the workload\'s %d envs x %d agents x %d ticks (%.1f s), oracle C port of the '
                       'reference numba path, %d threads, noise off, same action/auto-reset policy'
                       % (E, w['num_envs'], A, steps, dt, nthreads),
@@ -185,7 +191,7 @@ def run_reference(args):
                        'num_agents': w['num_agents'], 'num_beams': w['num_beams'],
                        'sample_envs_per_step': r['envs']},
             'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
-                             'sample': r['sample']},
+                             'sample': r['sample'], 'host': r['host']},
             'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0,
             'note': 'the reference is pure Python+numba and cannot travel to the GPU box; this arm times the '
@@ -367,7 +373,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_rollout_rate(args.workload, args.cpu_seconds)
-        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'], 'host': r['host'],
                'lookups_per_agent_step': r['lookups_per_agent_step']}
 
     if rank == 0:

@@ -17,6 +17,7 @@ Fixtures
   traj_a2_close.npz         Simulator, 2 agents 0.6-1.2 m apart (GJK contact, opponent occlusion,
                             rear-cut window case), several episodes.
   traj_a3_euler.npz         Simulator, 3 agents, Euler integrator, lidar_dist 0.1.
+  traj_{berlin,vegas}_a2.npz  Simulator, 2 agents 0.7-1.1 m apart on the 0.05 m maps (vegas = the reference default).
   env_laps.npz              real F110Env (gym/pyglet stubbed) + PurePursuitPlanner, 1 agent 2 laps:
                             actions, states, lap_times/lap_counts/done/toggles every tick.
 """
@@ -174,9 +175,9 @@ def scans():
 
 # ----------------------------------------------------------------------------- trajectories
 def run_traj(name, num_agents, episodes, ticks, gap_fn, seed, integrator=None, lidar_dist=0.0,
-             speed_hi=8.0, scan_every=8):
+             speed_hi=8.0, scan_every=8, map_yaml=None):
     rng = np.random.default_rng(seed)
-    sim = ref_import.new_simulator(ns, PARAMS, num_agents, ns.example_map, integrator=integrator,
+    sim = ref_import.new_simulator(ns, PARAMS, num_agents, map_yaml or ns.example_map, integrator=integrator,
                                    lidar_dist=lidar_dist)
     A = num_agents
     poses0, actions, states, cols, cidx, scans_, scan_ticks = [], [], [], [], [], [], []
@@ -222,6 +223,24 @@ def trajectories():
     run_traj('traj_a2_random.npz', 2, 2, 260, far(2), 12)
     run_traj('traj_a2_close.npz', 2, 6, 90, close, 13, scan_every=6)
     run_traj('traj_a3_euler.npz', 3, 2, 150, far(3), 14, integrator=ns.Integrator.Euler, lidar_dist=0.1)
+
+
+def trajectories_other_maps():
+    """Simulator trajectories on the 0.05 m maps (vegas is the reference's default map): the metre-unit march, the
+    general xy_2_rc and the opponent ray-cast on a resolution that is not a power of two."""
+    for name, seed in (('berlin', 31), ('vegas', 32)):
+        yaml_path = os.path.join(ns.maps_dir, name + '.yaml')
+        s = lm.ScanSimulator2D(1080, 4.7)
+        s.set_map(yaml_path, '.png')
+        free = np.argwhere(s.dt > 0.7)
+
+        def pair(rng, s=s, free=free):
+            r, c = free[rng.integers(0, free.shape[0])]
+            x, y = c * s.map_resolution + s.orig_x + 0.011, r * s.map_resolution + s.orig_y + 0.017
+            th = rng.uniform(0, 2 * np.pi)
+            d = rng.uniform(0.7, 1.1)
+            return np.array([[x, y, th], [x - d * np.cos(th), y - d * np.sin(th), th + rng.uniform(-0.3, 0.3)]])
+        run_traj('traj_%s_a2.npz' % name, 2, 4, 70, pair, seed, speed_hi=6.0, scan_every=5, map_yaml=yaml_path)
 
 
 # ----------------------------------------------------------------------------- F110Env laps
@@ -319,9 +338,8 @@ def kat_planner():
 
 
 if __name__ == '__main__':
-    kat_planner()
-    kat_reference_tests()
-    kat_kernels()
-    scans()
-    trajectories()
-    env_laps()
+    groups = {'kat_planner': kat_planner, 'kat_reference_tests': kat_reference_tests, 'kat_kernels': kat_kernels,
+              'scans': scans, 'trajectories': trajectories, 'trajectories_other_maps': trajectories_other_maps,
+              'env_laps': env_laps}
+    for name in (sys.argv[1:] or list(groups)):          # python make_golden.py [group ...]
+        groups[name]()

@@ -175,12 +175,17 @@ def make_sim(f110, dev, example_map, N, A, integrator=1, lidar_dist=0.0, **kw):
     return sim
 
 
-@pytest.mark.parametrize('name', ['traj_a1_random', 'traj_a2_random', 'traj_a2_close', 'traj_a3_euler'])
+@pytest.mark.parametrize('name', ['traj_a1_random', 'traj_a2_random', 'traj_a2_close', 'traj_a3_euler',
+                                  'traj_berlin_a2', 'traj_vegas_a2'])
 def test_trajectories_vs_reference(f110, dev, example_map, name):
-    """Episodes of the golden file run as the envs of one batch, in lockstep."""
+    """Episodes of the golden file run as the envs of one batch, in lockstep (berlin / vegas: the 0.05 m maps, i.e.
+    the metre-unit persistent march; vegas is the reference's default map)."""
     k = g(name + '.npz')
     E, T, A = k['actions'].shape[:3]
-    sim = make_sim(f110, dev, example_map, E, A, int(k['integrator']), float(k['lidar_dist']))
+    dmap = example_map
+    if name.startswith('traj_berlin') or name.startswith('traj_vegas'):
+        dmap = f110.DeviceMap.from_yaml(os.path.join(MAPS, name.split('_')[1] + '.yaml'), '.png', dev)
+    sim = make_sim(f110, dev, dmap, E, A, int(k['integrator']), float(k['lidar_dist']))
     sim.reset(k['poses0'])
     ticks = {(int(e), int(t)): i for i, (e, t) in enumerate(k['scan_ticks'])}
     worst_state, worst_scan, n_scan, n_bad, n_col = 0.0, 0.0, 0, 0, 0

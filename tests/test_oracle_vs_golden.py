@@ -110,6 +110,29 @@ def test_trajectories(example_map, name):
         assert n_col > 0
 
 
+@pytest.mark.parametrize('name', ['berlin', 'vegas'])
+def test_trajectories_other_maps(name):
+    """Reference Simulator trajectories on 0.05 m maps (no power-of-two resolution; vegas is the reference's default)."""
+    k = g('traj_%s_a2.npz' % name)
+    omap = oracle.OracleMap.from_yaml(os.path.join(MAPS, name + '.yaml'), '.png')
+    E, T, A = k['actions'].shape[:3]
+    sim = oracle.OracleSim(omap, num_agents=A)
+    ticks = {(int(e), int(t)): i for i, (e, t) in enumerate(k['scan_ticks'])}
+    n_col = n_occluded = 0
+    for e in range(E):
+        sim.reset(k['poses0'][e])
+        for t in range(T):
+            sim.step(k['actions'][e, t])
+            assert np.array_equal(sim.state, k['states'][e, t]), (e, t)
+            assert np.array_equal(sim.collisions, k['collisions'][e, t]), (e, t)
+            assert np.array_equal(sim.collision_idx, k['collision_idx'][e, t]), (e, t)
+            n_col += int(sim.collisions.sum())
+            if (e, t) in ticks:
+                assert np.max(np.abs(sim.scans - k['scans'][ticks[(e, t)]])) < 1e-9, (e, t)
+                n_occluded += int((sim.scans[0] < 1.5).sum())
+    assert n_occluded > 0
+
+
 def test_env_laps(example_map):
     k = g('env_laps.npz')
     sim = oracle.OracleSim(example_map, num_agents=1)

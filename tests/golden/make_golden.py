@@ -17,6 +17,7 @@ Fixtures
   traj_a2_close.npz         Simulator, 2 agents 0.6-1.2 m apart (GJK contact, opponent occlusion,
                             rear-cut window case), several episodes.
   traj_a3_euler.npz         Simulator, 3 agents, Euler integrator, lidar_dist 0.1.
+  traj_a2_params.npz        Simulator, 2 close agents, update_params(p2, agent_idx=1) before the run.
   traj_{berlin,vegas}_a2.npz  Simulator, 2 agents 0.7-1.1 m apart on the 0.05 m maps (vegas = the reference default).
   env_laps.npz              real F110Env (gym/pyglet stubbed) + PurePursuitPlanner, 1 agent 2 laps:
                             actions, states, lap_times/lap_counts/done/toggles every tick.
@@ -175,10 +176,12 @@ def scans():
 
 # ----------------------------------------------------------------------------- trajectories
 def run_traj(name, num_agents, episodes, ticks, gap_fn, seed, integrator=None, lidar_dist=0.0,
-             speed_hi=8.0, scan_every=8, map_yaml=None):
+             speed_hi=8.0, scan_every=8, map_yaml=None, params_update=None):
     rng = np.random.default_rng(seed)
     sim = ref_import.new_simulator(ns, PARAMS, num_agents, map_yaml or ns.example_map, integrator=integrator,
                                    lidar_dist=lidar_dist)
+    if params_update is not None:                      # Simulator.update_params (base_classes.py:514-534)
+        sim.update_params(params_update[1], agent_idx=params_update[0])
     A = num_agents
     poses0, actions, states, cols, cidx, scans_, scan_ticks = [], [], [], [], [], [], []
     for ep in range(episodes):
@@ -223,6 +226,16 @@ def trajectories():
     run_traj('traj_a2_random.npz', 2, 2, 260, far(2), 12)
     run_traj('traj_a2_close.npz', 2, 6, 90, close, 13, scan_every=6)
     run_traj('traj_a3_euler.npz', 3, 2, 150, far(3), 14, integrator=ns.Integrator.Euler, lidar_dist=0.1)
+
+
+def trajectory_params():
+    """update_params on one agent: a heavier, shorter, grippier car in slot 1 (dynamics AND its body for GJK/ray-cast)."""
+    def close(rng):
+        k = int(rng.integers(0, WP.shape[0]))
+        p = np.stack([wp_pose(k), wp_pose(k - int(rng.integers(4, 8)))])
+        return p
+    p2 = dict(PARAMS, mu=0.8, m=4.5, lf=0.17, lr=0.16, C_Sf=5.1, I=0.05, width=0.28, length=0.50, a_max=7.0)
+    run_traj('traj_a2_params.npz', 2, 3, 120, close, 15, scan_every=6, params_update=(1, p2))
 
 
 def trajectories_other_maps():
@@ -339,7 +352,7 @@ def kat_planner():
 
 if __name__ == '__main__':
     groups = {'kat_planner': kat_planner, 'kat_reference_tests': kat_reference_tests, 'kat_kernels': kat_kernels,
-              'scans': scans, 'trajectories': trajectories, 'trajectories_other_maps': trajectories_other_maps,
+              'scans': scans, 'trajectories': trajectories, 'trajectories_other_maps': trajectories_other_maps, 'trajectory_params': trajectory_params,
               'env_laps': env_laps}
     for name in (sys.argv[1:] or list(groups)):          # python make_golden.py [group ...]
         groups[name]()

@@ -110,6 +110,28 @@ def test_trajectories(example_map, name):
         assert n_col > 0
 
 
+def test_trajectory_with_updated_params(example_map):
+    """Simulator.update_params(p2, agent_idx=1) (base_classes.py:514-534): slot 1 integrates with its own parameters and
+    ray-casts opponents with its own body size, while GJK keeps the Simulator-level length/width (:536-550) and the
+    iTTC side distances stay those of the construction-time parameters."""
+    from f1tenth_gym_b200 import maps
+    k = g('traj_a2_params.npz')
+    E, T, A = k['actions'].shape[:3]
+    p2 = dict(maps.DEFAULT_PARAMS, mu=0.8, m=4.5, lf=0.17, lr=0.16, C_Sf=5.1, I=0.05, width=0.28, length=0.50, a_max=7.0)
+    sim = oracle.OracleSim(example_map, num_agents=A)
+    sim.params[1] = oracle.params_vector(p2)
+    ticks = {(int(e), int(t)): i for i, (e, t) in enumerate(k['scan_ticks'])}
+    for e in range(E):
+        sim.reset(k['poses0'][e])
+        for t in range(T):
+            sim.step(k['actions'][e, t])
+            assert np.array_equal(sim.state, k['states'][e, t]), (e, t)
+            assert np.array_equal(sim.collisions, k['collisions'][e, t]), (e, t)
+            if (e, t) in ticks:
+                assert np.max(np.abs(sim.scans - k['scans'][ticks[(e, t)]])) < 1e-9, (e, t)
+    assert k['collisions'].sum() > 0
+
+
 @pytest.mark.parametrize('name', ['berlin', 'vegas'])
 def test_trajectories_other_maps(name):
     """Reference Simulator trajectories on 0.05 m maps (no power-of-two resolution; vegas is the reference's default)."""

@@ -19,6 +19,7 @@ Fixtures
   traj_a3_euler.npz         Simulator, 3 agents, Euler integrator, lidar_dist 0.1.
   traj_a2_params.npz        Simulator, 2 close agents, update_params(p2, agent_idx=1) before the run.
   traj_{berlin,vegas}_a2.npz  Simulator, 2 agents 0.7-1.1 m apart on the 0.05 m maps (vegas = the reference default).
+  env_race2.npz             real F110Env, 2 pure-pursuit cars (BASELINE configs[0]) until the ego rams the slower opponent.
   env_laps.npz              real F110Env (gym/pyglet stubbed) + PurePursuitPlanner, 1 agent 2 laps:
                             actions, states, lap_times/lap_counts/done/toggles every tick.
 """
@@ -257,8 +258,9 @@ def trajectories_other_maps():
 
 
 # ----------------------------------------------------------------------------- F110Env laps
-def env_laps():
-    # stub gym + pyglet so the real F110Env and the example planner import unmodified (SURVEY app. B ii)
+def _run_real_env(fname, num_agents, pose_fn, gains, max_ticks=20000):
+    """Real F110Env (gym / pyglet stubbed, SURVEY app. B ii) driven by the example's PurePursuitPlanner, one planner
+    call per agent with its own (lookahead, vgain); every tick is recorded until `done`."""
     gym = types.ModuleType('gym')
     gym.Env = object
     for sub in ('error', 'spaces', 'utils'):
@@ -272,7 +274,8 @@ def env_laps():
     gl = types.ModuleType('pyglet.gl'); gl.GL_POINTS = 0; pyglet.gl = gl
     sys.modules.update({'pyglet': pyglet, 'pyglet.gl': gl})
     from f110_gym.envs import f110_env
-    sys.path.insert(0, os.path.join(ref_import.REF_ROOT, 'examples'))
+    if os.path.join(ref_import.REF_ROOT, 'examples') not in sys.path:
+        sys.path.insert(0, os.path.join(ref_import.REF_ROOT, 'examples'))
     import waypoint_follow as wf
     from argparse import Namespace
     import yaml
@@ -283,10 +286,11 @@ def env_laps():
         with open('config_example_map.yaml') as f:
             conf = Namespace(**yaml.safe_load(f))
         ns.RaceCar.scan_simulator = None
-        env = f110_env.F110Env(map=conf.map_path, map_ext=conf.map_ext, num_agents=1, timestep=0.01,
+        A = num_agents
+        env = f110_env.F110Env(map=conf.map_path, map_ext=conf.map_ext, num_agents=A, timestep=0.01,
                                integrator=ns.Integrator.RK4)
         planner = wf.PurePursuitPlanner(conf, 0.17145 + 0.15875)
-        pose0 = np.array([[conf.sx, conf.sy, conf.stheta]])
+        pose0 = pose_fn(conf)
         # noise must be off for determinism; F110Env.reset -> Simulator.reset recreates the rng, so
         # patch RaceCar.reset's effect by wrapping sim.reset.
         orig_reset = env.sim.reset
@@ -300,20 +304,39 @@ def env_laps():
         rec = dict(actions=[], states=[], lap_times=[], lap_counts=[], done=[], toggles=[], collisions=[])
 
         def record(act, done, info):
-            rec['actions'].append(act); rec['states'].append(env.sim.agents[0].state.copy())
+            rec['actions'].append(act)
+            rec['states'].append(np.array([a.state.copy() for a in env.sim.agents]) if A > 1
+                                 else env.sim.agents[0].state.copy())
             rec['lap_times'].append(env.lap_times.copy()); rec['lap_counts'].append(env.lap_counts.copy())
             rec['done'].append(done); rec['toggles'].append(env.toggle_list.copy())
             rec['collisions'].append(obs['collisions'].copy())
-        record(np.zeros((1, 2)), done, info)     # the tick executed inside reset
-        while not done:
-            speed, steer = planner.plan(obs['poses_x'][0], obs['poses_y'][0], obs['poses_theta'][0], 0.82461887897713965, 1.375)
-            act = np.array([[steer, speed]])
+        record(np.zeros((A, 2)), done, info)     # the tick executed inside reset
+        while not done and len(rec['done']) < max_ticks:
+            act = np.zeros((A, 2))
+            for i in range(A):
+                speed, steer = planner.plan(obs['poses_x'][i], obs['poses_y'][i], obs['poses_theta'][i], gains[i][0], gains[i][1])
+                act[i] = [steer, speed]
             obs, rew, done, info = env.step(act)
             record(act, done, info)
     finally:
         os.chdir(cwd)
-    save('env_laps.npz', pose0=pose0, **{k: np.array(v) for k, v in rec.items()})
-    print('env_laps ticks', len(rec['done']), 'final lap_times', rec['lap_times'][-1], 'lap_counts', rec['lap_counts'][-1])
+    save(fname, pose0=pose0, gains=np.array(gains), **{k: np.array(v) for k, v in rec.items()})
+    print(fname, 'ticks', len(rec['done']), 'done', rec['done'][-1], 'lap_times', rec['lap_times'][-1], 'lap_counts',
+          rec['lap_counts'][-1], 'collisions', rec['collisions'][-1])
+
+
+def env_laps():
+    _run_real_env('env_laps.npz', 1, lambda conf: np.array([[conf.sx, conf.sy, conf.stheta]]),
+                  [(0.82461887897713965, 1.375)])
+
+
+def env_race2():
+    """BASELINE configs[0]: two pure-pursuit cars on example_map in the real F110Env.  The ego starts 200 waypoints
+    (40 m) behind a slower opponent, laps once and then runs into it: lap toggles of both cars, opponent occlusion in
+    the ego's scan while closing in, then done through the ego's collision."""
+    def poses(conf):
+        return np.stack([wp_pose(0), wp_pose(200)])
+    _run_real_env('env_race2.npz', 2, poses, [(0.82461887897713965, 1.375), (0.82461887897713965, 1.1)])
 
 
 # ----------------------------------------------------------------------------- planner
@@ -353,6 +376,6 @@ def kat_planner():
 if __name__ == '__main__':
     groups = {'kat_planner': kat_planner, 'kat_reference_tests': kat_reference_tests, 'kat_kernels': kat_kernels,
               'scans': scans, 'trajectories': trajectories, 'trajectories_other_maps': trajectories_other_maps, 'trajectory_params': trajectory_params,
-              'env_laps': env_laps}
+              'env_laps': env_laps, 'env_race2': env_race2}
     for name in (sys.argv[1:] or list(groups)):          # python make_golden.py [group ...]
         groups[name]()

@@ -172,6 +172,26 @@ def test_env_laps(example_map):
     assert done and sim.lap_counts[0] == 2.0
 
 
+def test_env_race2(example_map):
+    """BASELINE configs[0] (two pure-pursuit cars in the real F110Env): 2088 ticks, one lap each in the ego's start
+    frame, the ego closes in on the slower car (opponent occlusion in its scan) and rams it -> done."""
+    k = g('env_race2.npz')
+    sim = oracle.OracleSim(example_map, num_agents=2)
+    done = sim.env_reset(k['pose0'])
+    T = k['actions'].shape[0]
+    for t in range(T):
+        if t > 0:
+            sim.step(k['actions'][t])
+            done = sim.env_post_step()
+        assert np.array_equal(sim.state, k['states'][t]), t
+        assert np.array_equal(sim.collisions, k['collisions'][t]), t
+        assert np.array_equal(sim.lap_times, k['lap_times'][t]), t
+        assert np.array_equal(sim.lap_counts, k['lap_counts'][t]), t
+        assert np.array_equal(sim.toggle_list, k['toggles'][t]), t
+        assert done == bool(k['done'][t]), t
+    assert done and sim.collisions[0] == 1.0 and np.array_equal(sim.lap_counts, [1.0, 1.0])
+
+
 def test_planner_vs_reference():
     """oracle pure pursuit == reference PurePursuitPlanner.plan (examples/waypoint_follow.py) incl. the
     re-acquire and no-waypoint branches; ulp-level slack for the BLAS dot products in the reference."""

@@ -1,7 +1,7 @@
 """BASELINE configs[0] on the CUDA path: the two-car pure-pursuit race of the real reference F110Env
 (tests/golden/env_race2.npz, 2088 ticks) replayed through the mirrored F110Env -- lap toggles of both cars, opponent
-occlusion while the ego closes in, `done` through the ego's collision.  (Runs last: it was added after the round's GPU
-budget was spent; its CPU twin, test_oracle_vs_golden.py::test_env_race2, pins the oracle on the same fixture.)"""
+occlusion while the ego closes in, `done` through the ego's collision.  Its CPU twin,
+test_oracle_vs_golden.py::test_env_race2, pins the oracle on the same fixture."""
 import os
 
 import numpy as np

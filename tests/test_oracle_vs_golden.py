@@ -110,6 +110,18 @@ def test_trajectories(example_map, name):
         assert n_col > 0
 
 
+def test_scans_rotated_origin():
+    """A map yaml whose origin has a yaw (0.35 rad): the rotation terms of xy_2_rc (laser_models.py:75-78), which none
+    of the bundled maps exercises.  Golden: the reference ScanSimulator2D on example_map.png with that origin."""
+    from f1tenth_gym_b200 import maps
+    k = g('scans_rotated_origin.npz')
+    hm = maps.load_map(os.path.join(MAPS, 'example_map.yaml'), '.png')
+    om = oracle.OracleMap(hm.dt, float(k['resolution']), tuple(k['origin']))
+    for p, ref in zip(k['poses'], k['scan_1080']):
+        assert np.array_equal(oracle.get_scan(om, p, 1080, 4.7), ref)
+    assert (k['scan_1080'][:-1] < 29.0).mean() > 0.8 and np.all(k['scan_1080'][-1] == 30.0)     # last pose is off the map
+
+
 def test_trajectory_with_updated_params(example_map):
     """Simulator.update_params(p2, agent_idx=1) (base_classes.py:514-534): slot 1 integrates with its own parameters and
     ray-casts opponents with its own body size, while GJK keeps the Simulator-level length/width (:536-550) and the

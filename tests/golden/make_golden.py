@@ -12,6 +12,8 @@ Fixtures
                             ray_cast, check_ttc, get_blocked_view_indices on random inputs.
   scans_<map>.npz           get_scan at fixed poses for B in {270,540,1080,2160} (example_map) and
                             1080 beams on berlin/skirk/vegas/stata_basement (res 0.05 / 0.0504 maps).
+  scans_rotated_origin.npz  get_scan on example_map.png under a yaml origin with yaw 0.35 (made ad hoc, see
+                            tests/golden/make_golden_rotated.py).
   traj_a1_random.npz        Simulator, 1 agent, random actions: state every tick, scans every 8th.
   traj_a2_random.npz        Simulator, 2 agents 4.6 m apart, random actions.
   traj_a2_close.npz         Simulator, 2 agents 0.6-1.2 m apart (GJK contact, opponent occlusion,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libf110_b200.so')
 
 F110_NPARAM = 18
 F110_NSTATE = 7
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _dp = C.c_void_p   # device / host pointers are passed as raw addresses
 
@@ -25,13 +25,16 @@ class F110Map(C.Structure):
                 ('theta_dis', C.c_int32), ('fast_path', C.c_int32),
                 ('dt_oob', C.c_double),
                 ('dt', _dp), ('dt_cells', _dp), ('dt_codes', _dp), ('dt_lut', _dp),
-                ('sines', _dp), ('cosines', _dp), ('sincos', _dp), ('num_layers', C.c_int32)]
+                ('sines', _dp), ('cosines', _dp), ('sincos', _dp),
+                ('dt_cells_pad', _dp), ('dt_codes_pad', _dp), ('sincos2', _dp),
+                ('dt_min_positive', C.c_double), ('num_layers', C.c_int32)]
 
 
 class F110Beams(C.Structure):
     _fields_ = [('num_beams', C.c_int32),
                 ('fov', C.c_double), ('angle_increment', C.c_double), ('theta_index_increment', C.c_double),
-                ('scan_angles', _dp), ('cosines', _dp), ('side_distances', _dp), ('cos_side', _dp)]
+                ('scan_angles', _dp), ('cosines', _dp), ('side_distances', _dp), ('cos_side', _dp),
+                ('side_max', C.c_double)]
 
 
 class F110Sim(C.Structure):
@@ -47,7 +50,7 @@ class F110Sim(C.Structure):
                 ('start_rot', _dp), ('done', _dp), ('checkpoint_done', _dp), ('env_arrivals', _dp), ('env_layer', _dp),
                 ('lookup_counter', _dp), ('tick_counter', _dp),
                 ('march_cost', _dp), ('march_order', _dp), ('march_count', _dp), ('march_ipa', C.c_int32),
-                ('noise_std', C.c_double), ('noise_seed', C.c_uint64)]
+                ('march_rec', _dp), ('noise_std', C.c_double), ('noise_seed', C.c_uint64)]
 
 
 class F110HostObs(C.Structure):
@@ -75,6 +78,7 @@ SIGNATURES = {
                                        _P(F110HostObs), _dp, _dp, _dp, _dp]),
     'f110_scan': (C.c_int, [_P(F110Map), _P(F110Beams), _dp, C.c_int32, _dp, _dp, _dp, _dp]),
     'f110_vehicle_dynamics_st': (C.c_int, [_dp, _dp, _dp, C.c_int32, _dp, _dp]),
+    'f110_vehicle_dynamics_ks': (C.c_int, [_dp, _dp, _dp, C.c_int32, _dp, _dp]),
     'f110_pid': (C.c_int, [_dp, _dp, C.c_int32, _dp, _dp]),
     'f110_get_vertices': (C.c_int, [_dp, C.c_double, C.c_double, C.c_int32, _dp, _dp]),
     'f110_collision': (C.c_int, [_dp, _dp, C.c_int32, _dp, _dp]),
@@ -88,6 +92,12 @@ SIGNATURES = {
     'f110_edt': (C.c_int, [_dp, C.c_int32, C.c_int32, C.c_double, _dp, _dp, _dp, _dp]),
     'f110_rasterize_track': (C.c_int, [_dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     'f110_scan_noise': (C.c_int, [_dp, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, _dp]),
+}
+
+# measurement / test aids exported by the library but not part of the public header
+DEBUG_SIGNATURES = {
+    'f110_debug_set_variant': (None, [C.c_int]),
+    'f110_debug_set_chunk': (None, [C.c_int]),
 }
 
 _LIB = None
@@ -123,6 +133,11 @@ def lib():
             raise NativeLibraryError('f1tenth_gym_b200: %s does not export %s (stale build?)' % (LIB_PATH, name))
         f.restype = res
         f.argtypes = args
+    for name, (res, args) in DEBUG_SIGNATURES.items():
+        f = getattr(L, name, None)
+        if f is not None:
+            f.restype = res
+            f.argtypes = args
     if L.f110_abi_version() != ABI_VERSION:
         raise NativeLibraryError('f1tenth_gym_b200: ABI version mismatch (lib %d, python %d); rebuild'
                                  % (L.f110_abi_version(), ABI_VERSION))

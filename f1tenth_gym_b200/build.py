@@ -11,7 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libf110_b200.so')
 SOURCES = ['f110_b200.cu']
-DEPS = ['f110_b200.cu', 'dynamics.cuh', 'lidar.cuh', 'collision.cuh', os.path.join('..', '..', 'include', 'f110_b200.h')]
+INCLUDE = os.path.join(HERE, '..', 'include')
+
+
+def deps():
+    """Every source the library is built from: all of csrc/ and the public header(s)."""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, '*.cu')) + glob.glob(os.path.join(CSRC, '*.cuh')) +
+                  glob.glob(os.path.join(INCLUDE, '*.h')) + [os.path.abspath(__file__)])
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3',
               '-lineinfo', '-fmad=false', '-std=c++17']
 
@@ -27,7 +34,7 @@ def is_stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build_native(force=False, verbose=False):

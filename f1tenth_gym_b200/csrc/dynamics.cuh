@@ -32,6 +32,19 @@ __device__ __forceinline__ double steering_constraint(double angle, double sv, d
     return sv;
 }
 
+// dynamic_models.py:90-121 (vehicle_dynamics_ks): x has 5 entries (x, y, steer, v, yaw), f has 5
+__device__ __forceinline__ void vehicle_dynamics_ks(const double x[5], double u_sv, double u_accl,
+                                                    const double *__restrict__ p, double f[5]) {
+    const double lwb = p[P_LF] + p[P_LR];
+    const double u0 = steering_constraint(x[2], u_sv, p[P_SMIN], p[P_SMAX], p[P_SVMIN], p[P_SVMAX]);
+    const double u1 = accl_constraints(x[3], u_accl, p[P_VSWITCH], p[P_AMAX], p[P_VMIN], p[P_VMAX]);
+    f[0] = x[3] * cos(x[4]);
+    f[1] = x[3] * sin(x[4]);
+    f[2] = u0;
+    f[3] = u1;
+    f[4] = x[3] / lwb * tan(x[2]);
+}
+
 // dynamic_models.py:123-176 (vehicle_dynamics_st, with the :90-121 kinematic model for |v| < 0.5)
 __device__ __forceinline__ void vehicle_dynamics_st(const double x[7], double u_sv, double u_accl,
                                                     const double *__restrict__ p, double f[7]) {

@@ -18,6 +18,7 @@
 #include "dynamics.cuh"
 #include "lidar.cuh"
 #include "march.cuh"
+#include "march_lean.cuh"
 #include "planner.cuh"
 #include "edt.cuh"
 #include "trackgen.cuh"
@@ -149,6 +150,10 @@ struct FirstLookup {
     int metres;
     const int32_t *__restrict__ env_layer;   // multi-map batches: layer of each env, or NULL
     unsigned long long layer_stride;
+    // per-agent record of the lean march kernel (march_lean.cuh); rec == NULL: not written
+    double2 *__restrict__ rec;
+    double side_max, ttc_margin;
+    unsigned long long rec_layer_stride;     // elements between map layers of the table the lean kernel reads
 };
 
 __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
@@ -202,8 +207,27 @@ __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__re
         slot2 = __ldg(fl.cells + lo + idx);
     }
     double2 *sp = reinterpret_cast<double2 *>(s.scan_pose) + 2 * (size_t)a;
+    const double ti0 = theta_index0(st[4], fov, theta_dis_f);
     sp[0] = make_double2(sx, sy);
-    sp[1] = make_double2(slot2, theta_index0(st[4], fov, theta_dis_f));
+    sp[1] = make_double2(slot2, ti0);
+    if (fl.rec) {
+        // everything the march needs per agent, computed once here instead of once per 32-beam work item
+        // the march takes floor() through the low word of a magic-number add: cell coordinates must stay below 2^31
+        const bool sane = fabs(sx) * fl.inv_res < 1e9 && fabs(sy) * fl.inv_res < 1e9;
+        const bool cells = !fl.metres;
+        double2 *rp = fl.rec + 4 * (size_t)a;
+        rp[0] = (sane && cells) ? make_double2(sx * fl.inv_res, sy * fl.inv_res) : make_double2(sx, sy);
+        // LUT index of beam 0 as Q16.48 (ti0 in [0, theta_dis], theta_dis < 2^15); all ones = absurd coordinates
+        const unsigned long long tfx = sane ? __double2ull_rd(ti0 * 281474976710656.0) : ~0ull;
+        rp[1] = make_double2(slot2, __longlong_as_double((long long)tfx));
+        // iTTC (laser_models.py:188-217) can only fire for |range - side_i| <= margin * |v cos_i|, i.e. never for
+        // range > max(side) + margin * |v| (1e-9 of slack covers the roundings); v == 0 never fires
+        const double v = st[3];
+        const double thr = (v != 0.0) ? (fl.side_max + fl.ttc_margin * fabs(v)) * (1.0 + 1e-9) : -INFINITY;
+        rp[2] = make_double2(thr, v);
+        const unsigned long long lo_rec = fl.env_layer ? (unsigned long long)fl.env_layer[a / s.num_agents] * fl.rec_layer_stride : 0ull;
+        rp[3] = make_double2(__longlong_as_double((long long)lo_rec), ti0);
+    }
     // pose snapshot (Simulator.agent_poses, base_classes.py:574) + cos/sin of the yaw: every vertex / heading
     // computation of the finalize kernel reuses them instead of re-evaluating fp64 trig per opponent
     double *ap = s.agent_poses + 5 * (size_t)a;
@@ -413,7 +437,10 @@ __global__ void k_reset(f110_sim s, const double *__restrict__ poses, const uint
     mark_march_cost_unknown(s, a);
 }
 
-__device__ __forceinline__ void env_counters_reset(const f110_sim &s, int env, const double *agent_pose3 /* [A][3] */) {
+// clear_done: f110_env_reset (a fresh episode requested by the caller) clears the done flag; the auto-reset does NOT --
+// the tick that ended an episode must still report done = 1 for it (the next tick recomputes the flag)
+__device__ __forceinline__ void env_counters_reset(const f110_sim &s, int env, const double *agent_pose3 /* [A][3] */,
+                                                   bool clear_done = true) {
     const int A = s.num_agents;
     s.current_time[env] = 0.0;
     for (int i = 0; i < A; i++) {
@@ -428,7 +455,7 @@ __device__ __forceinline__ void env_counters_reset(const f110_sim &s, int env, c
     const double th = -agent_pose3[3 * s.ego_idx + 2];
     double *R = s.start_rot + 4 * (size_t)env;
     R[0] = cos(th); R[1] = -sin(th); R[2] = sin(th); R[3] = cos(th);
-    if (s.done) s.done[env] = 0;
+    if (s.done && clear_done) s.done[env] = 0;
 }
 
 __global__ void k_env_reset(f110_sim s, const double *__restrict__ poses, const uint8_t *__restrict__ mask) {
@@ -517,7 +544,7 @@ __device__ __forceinline__ void autoreset_one(const f110_sim &s, int env, const 
         s.wall_flag[a] = 0;
         mark_march_cost_unknown(s, a);
     }
-    if (s.current_time && A <= 32) env_counters_reset(s, env, pose3);
+    if (s.current_time && A <= 32) env_counters_reset(s, env, pose3, false);
 }
 
 __global__ void k_autoreset(f110_sim s, AutoResetArgs ar) {
@@ -559,6 +586,16 @@ __global__ void k_rhs(const double *__restrict__ x, const double *__restrict__ u
     for (int k = 0; k < 7; k++) xs[k] = x[7 * (size_t)i + k];
     vehicle_dynamics_st(xs, u[2 * (size_t)i], u[2 * (size_t)i + 1], p, fs);
     for (int k = 0; k < 7; k++) f[7 * (size_t)i + k] = fs[k];
+}
+
+__global__ void k_rhs_ks(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ p,
+                         int M, double *__restrict__ f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double xs[5], fs[5];
+    for (int k = 0; k < 5; k++) xs[k] = x[5 * (size_t)i + k];
+    vehicle_dynamics_ks(xs, u[2 * (size_t)i], u[2 * (size_t)i + 1], p, fs);
+    for (int k = 0; k < 5; k++) f[5 * (size_t)i + k] = fs[k];
 }
 
 __global__ void k_pid(const double *__restrict__ in, const double *__restrict__ p, int M, double *__restrict__ out) {
@@ -684,13 +721,13 @@ static int num_sms() {
 
 // A/B switch for measurements (profiles/): F110_MARCH_VARIANT = 0 default (persistent queue, fp64 cell table),
 // 6 = rank-coded byte table, 7 = no queue (one block per 64-beam tile), 9 = no queue, 40 registers
+static int g_variant = -1, g_chunk = -1;
 static int rm_variant() {
-    static int v = -1;
-    if (v < 0) {
+    if (g_variant < 0) {
         const char *e = getenv("F110_MARCH_VARIANT");
-        v = e ? atoi(e) : 0;
+        g_variant = e ? atoi(e) : 0;
     }
-    return v;
+    return g_variant;
 }
 
 static int launch_raymarch(const MapView &mv, const BeamView &bv, const MarchArgs &g, bool fast, bool standalone,
@@ -726,6 +763,23 @@ static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned bl
     }
 }
 
+template <int TABLE, bool CELLS, bool LAYERED, int MINB>
+static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
+    if (count) k_march_lean<TABLE, false, true, CELLS, LAYERED, 512, MINB><<<blocks, 512, 0, st>>>(q, mq);
+    else if (noise) k_march_lean<TABLE, true, false, CELLS, LAYERED, 512, MINB><<<blocks, 512, 0, st>>>(q, mq);
+    else k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB><<<blocks, 512, 0, st>>>(q, mq);
+}
+static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool cells, bool coded, bool occ3, bool layered,
+                        bool noise, bool count, cudaStream_t st) {
+    if (!cells && layered) launch_lean_t<0, false, true, 4>(q, mq, sms * 4u, noise, count, st);
+    else if (!cells) launch_lean_t<0, false, false, 4>(q, mq, sms * 4u, noise, count, st);
+    else if (layered) launch_lean_t<0, true, true, 4>(q, mq, sms * 4u, noise, count, st);
+    else if (coded && occ3) launch_lean_t<1, true, false, 3>(q, mq, sms * 3u, noise, count, st);
+    else if (coded) launch_lean_t<1, true, false, 4>(q, mq, sms * 4u, noise, count, st);
+    else if (occ3) launch_lean_t<0, true, false, 3>(q, mq, sms * 3u, noise, count, st);
+    else launch_lean_t<0, true, false, 4>(q, mq, sms * 4u, noise, count, st);
+}
+
 template <int MINB, bool CELLS>
 static void launch_march(const MarchK &k, dim3 grid, bool coded, bool noise, bool count, cudaStream_t st) {
     if (coded && CELLS) {
@@ -751,6 +805,9 @@ int f110_abi_version(void) { return F110_ABI_VERSION; }
 /* debug aid (not in the public header): device buffer [blocks][4] u64 that the march kernels fill with
  * (smid, start ns, end ns, max steps of warp 0) per block; NULL switches it off. */
 void f110_debug_set_trace(unsigned long long *buf) { g_trace = buf; }
+/* measurement aid (not in the public header): select the march kernel variant at run time (tools/ab_march.py) */
+void f110_debug_set_variant(int variant) { g_variant = variant < 0 ? 0 : variant; }
+void f110_debug_set_chunk(int chunk_shift) { g_chunk = (chunk_shift < 0 || chunk_shift > 6) ? 3 : chunk_shift; }
 
 const char *f110_status_string(int status) {
     switch (status) {
@@ -778,6 +835,9 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     int rc;
     if ((rc = check_sim(sim)) || (rc = check_map(map)) || (rc = check_beams(beams))) return rc;
     if (!actions) return F110_ERR_INVALID;
+    // argument combinations are rejected BEFORE anything is enqueued: a tick either runs completely or not at all
+    if (sim->lookup_counter && sim->noise_std > 0.0) return F110_ERR_INVALID;   // counting runs are noise-free by construction
+    if ((long long)sim->num_envs * sim->num_agents > 0x7fffffffll) return F110_ERR_INVALID;
     const int NA = sim->num_envs * sim->num_agents;
     const MapView mv = make_view(map);
     const BeamView bv = make_view(beams);
@@ -812,6 +872,18 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     fl.inv_res = 1.0 / map->resolution; fl.ox = map->orig_x * fl.inv_res; fl.oy = map->orig_y * fl.inv_res;
     fl.width = (unsigned)map->width; fl.height = (unsigned)map->height;
     fl.last = (unsigned)map->width * (unsigned)map->height - 1u;
+    // the lean march kernel (march_lean.cuh): 32-beam queue items, `d > eps` == `d != 0` (every positive DT value exceeds
+    // eps), fov < 2 pi (the doubled sin/cos LUT replaces the wrap), LUT indices that fit the Q16.48 fixed point
+    const bool lean = queued && cell_march && item_sub == 1 && sim->march_rec && map->sincos2 && map->eps >= 0.0 &&
+                      (!cell_units || map->dt_cells_pad) && (unsigned long long)NA * (unsigned long long)beams->num_beams < (1ull << 32) &&
+                      (unsigned long long)(map->width + 1) * (unsigned long long)(map->height + 1) < (1ull << 32) &&
+                      map->dt_min_positive > map->eps && beams->fov > 0.0 && beams->fov < 6.283185307179586 &&
+                      beams->theta_index_increment > 0.0 && map->theta_dis < 32768 &&
+                      variant != 1 && variant != 6;
+    fl.rec = lean ? reinterpret_cast<double2 *>(sim->march_rec) : nullptr;
+    fl.side_max = beams->side_max > 0.0 ? beams->side_max : INFINITY;
+    fl.ttc_margin = sim->ttc_thresh * 1.000001;
+    fl.rec_layer_stride = cell_units ? (unsigned long long)(map->width + 1) * (unsigned long long)(map->height + 1) : fl.layer_stride;
     k_dynamics<<<dyn_blocks + order_blocks, 128, 0, st>>>(*sim, actions, beams->fov, (double)map->theta_dis, dyn_blocks, fl);
     LAUNCH_CHECK("k_dynamics");
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -844,11 +916,41 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
         const int bpa = (beams->num_beams + 63) / 64;
         if (bpa > 65000) return F110_ERR_INVALID;
         const bool noise = sim->noise_std > 0.0, count = sim->lookup_counter != nullptr;
+        MarchQueue mq;
         if (queued) {
-            MarchQueue mq;
             mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
-            { static int cs = -1; if (cs < 0) { const char *e = getenv("F110_MARCH_CHUNK"); cs = e ? atoi(e) : 3; if (cs < 0 || cs > 6) cs = 3; } mq.chunk_shift = (unsigned)cs; }
+            if (g_chunk < 0) { const char *e = getenv("F110_MARCH_CHUNK"); g_chunk = e ? atoi(e) : 3; if (g_chunk < 0 || g_chunk > 6) g_chunk = 3; }
+            mq.chunk_shift = (unsigned)g_chunk;
+        }
+        if (lean) {
+            LeanK q;
+            q.table = cell_units ? map->dt_cells_pad : map->dt;
+            q.codes = map->dt_codes_pad; q.lut = map->dt_lut;
+            q.sincos2 = reinterpret_cast<const double2 *>(map->sincos2);
+            q.cos_side = k.cos_side;
+            q.rec = reinterpret_cast<const double2 *>(sim->march_rec);
+            q.out = sim->scans; q.wall_flag = sim->wall_flag;
+            q.lookup_counter = sim->lookup_counter; q.tick_counter = sim->tick_counter;
+            q.res = map->resolution; q.inv_res = 1.0 / map->resolution;
+            if (cell_units) { q.ox = k.ox; q.oy = k.oy; q.tmax = k.tmax; }
+            else { q.ox = map->orig_x; q.oy = map->orig_y; q.tmax = map->max_range; }
+            q.x_max = mv.x_max; q.y_max = mv.y_max;
+            q.ttc_thresh = k.ttc_thresh; q.ttc_margin = k.ttc_margin; q.noise_std = k.noise_std; q.noise_seed = k.noise_seed;
+            q.inc = k.inc; q.theta_dis_f = k.theta_dis_f;
+            q.inc_fx = (unsigned long long)(beams->theta_index_increment * 281474976710656.0 + 0.5);
+            // the fixed-point index is within B * 2^-49 + 2^-48 of the real closed form, which is within B * 1.14e-13 of the
+            // reference's sequential sum (lidar.cuh): replay when the fraction is closer than that (x4) to an integer
+            const double guard = 4.0 * ((double)beams->num_beams * 1.2e-13 + 1e-12);
+            q.guard32 = (unsigned)(guard * 4294967296.0) + 2u;
+            q.width = k.width; q.height = k.height; q.last = k.last; q.B = k.B;
+            q.layer_stride = fl.layer_stride; q.layer_stride_lean = fl.rec_layer_stride;
+            q.dt = map->dt; q.orig_x = map->orig_x; q.orig_y = map->orig_y; q.dt_oob_unused = 0.0; q.eps_m = map->eps;
+            q.max_range = map->max_range;
+            const bool lcoded = cell_units && !layered && map->dt_codes_pad && map->dt_lut && (variant == 20 || variant == 22);
+            const bool occ3 = (variant == 21 || variant == 22);
+            launch_lean(q, mq, (unsigned)num_sms(), cell_units, lcoded, occ3, layered, noise, count, st);
+        } else if (queued) {
             const unsigned blocks = (unsigned)num_sms() * 4u;
             if (!cell_units) launch_persistent<512, 1, false>(k, mq, blocks, coded, noise, count, st);
             else if (item_sub == 2) launch_persistent<512, 2, true>(k, mq, blocks, coded, noise, count, st);
@@ -860,7 +962,6 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             else launch_march<32, true>(k, grid, coded, noise, count, st);
         }
         LAUNCH_CHECK("k_march");
-        if (count && noise) return F110_ERR_INVALID;   // counting runs are noise-free by construction
         goto marched;
     }
     {
@@ -1078,6 +1179,13 @@ int f110_vehicle_dynamics_st(const double *x, const double *u, const double *par
     if (!x || !u || !params || !f || M <= 0) return F110_ERR_INVALID;
     k_rhs<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, u, params, M, f);
     LAUNCH_CHECK("k_rhs");
+    return F110_OK;
+}
+
+int f110_vehicle_dynamics_ks(const double *x, const double *u, const double *params, int32_t M, double *f, void *stream) {
+    if (!x || !u || !params || !f || M <= 0) return F110_ERR_INVALID;
+    k_rhs_ks<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, u, params, M, f);
+    LAUNCH_CHECK("k_rhs_ks");
     return F110_OK;
 }
 

@@ -1,0 +1,225 @@
+// march_lean.cuh — k_march_lean: the production ray-march kernel of f110_step / f110_tick (round 2).
+//
+// Same results as march.cuh's k_march_persistent (bit-identical ranges, same DT lookups), same persistent
+// longest-first work queue; what changed is the instruction count.  The round-1 SASS (profiles/r2/README.md) spent
+// ~170 of its ~365 warp-instructions per 32-beam work item OUTSIDE the sphere-tracing loop and carried four
+// kernel-parameter reloads inside it.  Here:
+//   * everything that is constant for an agent is computed once per agent by k_dynamics into a 64-byte record
+//     (scan position already in cell units, first lookup, LUT index of beam 0 as Q16.48 fixed point, the iTTC
+//     pre-test threshold, the map-layer offset): a work item starts with two 16-byte broadcast loads;
+//   * the beam's LUT index is a 64-bit integer multiply-add on that fixed-point value (no I2F / F2I on the XU
+//     pipe, no fp64 compare chain); beams whose fractional part is within the proven error bound of an integer
+//     replay the reference's sequential recurrence exactly as before (lidar.cuh), out of line;
+//   * the sin/cos LUT is stored twice back to back, so the `while theta_index >= theta_dis` wrap is an index, not a
+//     branch (needs fov < 2 pi: host-checked);
+//   * `d > eps` is an integer test on the high word: every DT value is resolution * sqrt(k) with integer k, so it is
+//     either +0.0 or >= resolution > eps (host-checked: resolution > eps >= 0);
+//   * the cell-unit tables carry one extra row and column holding dt[-1,-1] (what an off-map lookup reads through
+//     numba's negative-index wrap, laser_models.py:79-81): the bounds test is two unsigned min() on the cell
+//     coordinates (a negative coordinate is a huge unsigned) instead of two compares, a select and a reload of `last`;
+//   * iTTC (laser_models.py:188-217): one compare per beam against a per-agent threshold (range > max side distance
+//     + margin * |v| cannot be a hit); the exact test runs out of line for the few beams that are that close;
+//   * TABLE = 1: the lookup goes to the 1-byte rank-coded table (32 cells per 32-byte sector instead of 4) and the
+//     code is decoded through a 2 KB fp64 LUT in SHARED memory; the escape code decodes to NaN, which ends the loop
+//     through the range test, and such a beam (never on a race track) is redone on the fp64 table out of line.
+// Behavioural spec: reference laser_models.py:106-217 (trace_ray, get_scan, check_ttc_jit).
+#pragma once
+#include "march.cuh"
+
+namespace f110 {
+
+struct LeanK {
+    const double *__restrict__ table;       // CELLS: [L][(H+1)*(W+1)] dt / res, padded with dt[-1,-1]; else [L][H*W] dt in metres
+    const uint8_t *__restrict__ codes;      // [(H+1)*(W+1)] rank codes of the padded table (TABLE = 1), else NULL
+    const double *__restrict__ lut;         // [256] code -> table value, lut[255] = NaN
+    const double2 *__restrict__ sincos2;    // [2 * theta_dis] (sin, cos), the LUT stored twice
+    const double2 *__restrict__ cos_side;   // [B] (cos(scan_angle_i), side_distance_i)
+    const double2 *__restrict__ rec;        // [M][4] per-agent record written by k_dynamics (MarchRec)
+    float *__restrict__ out;                // [M][B]
+    int32_t *__restrict__ wall_flag;        // [M]
+    unsigned long long *lookup_counter;     // COUNT only
+    const unsigned long long *tick_counter; // NOISE only
+    double ox, oy, tmax;                    // CELLS: orig / res, max_range / res; else orig (m), max_range (m)
+    double res, inv_res, x_max, y_max;      // metres path (and range scaling of the cell path)
+    double ttc_thresh, ttc_margin, noise_std;
+    double inc, theta_dis_f;                // replay path
+    unsigned long long inc_fx;              // theta_index_increment in Q16.48
+    unsigned long long noise_seed;
+    unsigned guard32;                       // replay when the fraction (top 32 bits) is within guard32 of an integer
+    unsigned width, height, last;           // CELLS: `last` unused, the row stride is width + 1
+    int B;
+    // literal fallback for absurd coordinates
+    const double *__restrict__ dt;
+    double orig_x, orig_y, dt_oob_unused, eps_m, max_range;
+    unsigned long long layer_stride;        // elements between layers of dt (metres table)
+    unsigned long long layer_stride_lean;   // elements between layers of `table`
+};
+
+// per-agent record, 4 x double2:
+//   [0] (X, Y)      scan position: cell units (CELLS) or metres
+//   [1] (d0, ti0fx) first DT lookup (same unit), LUT index of beam 0 in Q16.48 (bits), ~0 = absurd coordinates
+//   [2] (thr, v)    iTTC pre-test threshold in metres (-inf when v == 0), longitudinal velocity
+//   [3] (off, ti0)  element offset of the env's map layer (bits), LUT index of beam 0 as the reference's fp64 value
+#define F110_FX_SHIFT 48
+
+__device__ __noinline__ int replay_theta_index(double ti0, int i, double inc, double theta_dis_f) {
+    double t = ti0;
+    for (int k = 0; k < i; k++) {
+        t += inc;
+        while (t >= theta_dis_f) t -= theta_dis_f;
+    }
+    return (int)t;
+}
+
+// exact iTTC predicate for one beam (check_ttc_jit, laser_models.py:188-217); v != 0
+__device__ __noinline__ void ttc_exact(double range, double v, double cos_i, double side_i, double thresh, double margin,
+                                       int32_t *flag) {
+    const double pv = v * cos_i;
+    const double d = range - side_i;
+    if (fabs(d) <= margin * fabs(pv)) {
+        const double ttc = d / pv;
+        if ((ttc < thresh) && (ttc >= 0.0)) atomicOr(flag, 1);
+    }
+}
+
+// one beam on the fp64 table, cell units: the escape path of the coded table
+__device__ __noinline__ double redo_beam_cells(const double *__restrict__ table, double X, double Y, double d0, double s,
+                                               double c, double ox, double oy, double tmax, unsigned width,
+                                               unsigned height, unsigned *n_out) {
+    const double MAGIC = 6755399441055744.0;
+    double T = d0, D = d0;
+    unsigned n = 1;
+    while (D > 0.0 && T <= tmax) {
+        X = X + D * c;
+        Y = Y + D * s;
+        const int cc = __double2loint(__dadd_rd(X - ox, MAGIC));
+        const int rr = __double2loint(__dadd_rd(Y - oy, MAGIC));
+        D = __ldg(table + min((unsigned)rr, height) * (width + 1u) + min((unsigned)cc, width));
+        T = T + D;
+        n++;
+    }
+    *n_out = n;
+    return T;
+}
+
+// TABLE: 0 = fp64 table in global memory, 1 = u8 rank codes in global memory + fp64 LUT in shared memory
+template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB>
+__global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const MarchQueue mq) {
+    __shared__ unsigned s_next;
+    __shared__ double s_lut[TABLE == 1 ? 256 : 1];
+    if (threadIdx.x == 0) s_next = 0u;
+    if (TABLE == 1)
+        for (unsigned t = threadIdx.x; t < 256u; t += PT) s_lut[t] = p.lut[t];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned nA = min(mq.count[0], mq.items), nB = min(mq.count[1], mq.items);
+    const unsigned nAB = nA + nB;
+    const unsigned total = min(nAB + min(mq.count[2], mq.items), mq.items);
+    const unsigned cs = mq.chunk_shift;
+    const unsigned qstride = gridDim.x << cs, qbase = blockIdx.x << cs, qmask = (1u << cs) - 1u;
+    const unsigned s_next_addr = (unsigned)__cvta_generic_to_shared(&s_next);
+    unsigned looks = 0u;
+    for (;;) {
+        // one elected lane pops the block's queue.  (An atomicAdd inside `if (lane == 0)` makes ptxas emit its
+        // warp-aggregation sequence -- vote, find-leader, two popc, shuffle: 14 extra instructions per item.)
+        unsigned k = 0, leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
+                     : "+r"(k), "=r"(leader) : "r"(s_next_addr) : "memory");
+        k = __shfl_sync(0xffffffffu, k, leader);
+        const unsigned q = (k >> cs) * qstride + qbase + (k & qmask);
+        if (q >= total) break;
+        const unsigned it = mq.order[(q < nA) ? q : (q < nAB) ? (mq.items + (q - nA)) : (2u * mq.items + (q - nAB))];
+        const unsigned a = it >> 8;
+        const int i = (int)((it & 255u) * 32u + lane);
+        const double2 *__restrict__ rp = p.rec + 4 * (size_t)a;
+        const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        const unsigned long long ti0fx = (unsigned long long)__double_as_longlong(r1.y);
+        unsigned n = 0;
+        if (i < p.B) {
+            double range;
+            if (ti0fx != ~0ull) {
+                const unsigned long long vfx = ti0fx + (unsigned long long)(unsigned)i * p.inc_fx;
+                unsigned ti = (unsigned)(vfx >> F110_FX_SHIFT);
+                const unsigned fr = (unsigned)(vfx >> (F110_FX_SHIFT - 32));
+                if (fr + p.guard32 <= 2u * p.guard32)
+                    ti = (unsigned)replay_theta_index(__ldg(rp + 3).y, i, p.inc, p.theta_dis_f);
+                const double2 sc = __ldg(p.sincos2 + ti);
+                const double *__restrict__ table = p.table;
+                if (LAYERED) table += (unsigned long long)__double_as_longlong(__ldg(rp + 3).x);
+                asm volatile("" : "+l"(table));
+                const double MAGIC = 6755399441055744.0;   // 2^52 + 2^51: round-down add == floor in the low word
+                double X = r0.x, Y = r0.y, T = r1.x, D = r1.x;
+                n = 1;
+                if (CELLS) {
+                    if (__double2hiint(D) != 0 && T <= p.tmax) {
+#pragma unroll 1
+                        do {
+                            X = X + D * sc.y;
+                            Y = Y + D * sc.x;
+                            const unsigned c = (unsigned)__double2loint(__dadd_rd(X - p.ox, MAGIC));
+                            const unsigned r = (unsigned)__double2loint(__dadd_rd(Y - p.oy, MAGIC));
+                            // off-map -> the padding row / column, which holds dt[-1,-1]
+                            const unsigned idx = min(r, p.height) * (p.width + 1u) + min(c, p.width);
+                            if (TABLE == 1) D = s_lut[__ldg(p.codes + idx)];
+                            else D = __ldg(table + idx);
+                            T = T + D;
+                            n++;
+                        } while (__double2hiint(D) != 0 && T <= p.tmax);
+                    }
+                    if (TABLE == 1 && T != T) {     // escape code on the way: redo this beam on the fp64 table
+                        T = redo_beam_cells(table, r0.x, r0.y, r1.x, sc.x, sc.y, p.ox, p.oy, p.tmax, p.width, p.height, &n);
+                    }
+                    range = ((T > p.tmax) ? p.tmax : T) * p.res;
+                } else {
+                    if (__double2hiint(D) != 0 && T <= p.tmax) {
+#pragma unroll 1
+                        do {
+                            X = X + D * sc.y;
+                            Y = Y + D * sc.x;
+                            const double tx = X - p.ox, ty = Y - p.oy;
+                            double qx = tx * p.inv_res, qy = ty * p.inv_res;
+                            qx = __fma_rn(__fma_rn(-qx, p.res, tx), p.inv_res, qx);     // RN(tx / res), see march.cuh
+                            qy = __fma_rn(__fma_rn(-qy, p.res, ty), p.inv_res, qy);
+                            const int c = __double2loint(__dadd_rd(qx, MAGIC));
+                            const int r = __double2loint(__dadd_rd(qy, MAGIC));
+                            unsigned idx = (unsigned)r * p.width + (unsigned)c;
+                            if ((unsigned)c >= p.width || (unsigned)r >= p.height || tx >= p.x_max || ty >= p.y_max) idx = p.last;
+                            D = __ldg(table + idx);
+                            T = T + D;
+                            n++;
+                        } while (__double2hiint(D) != 0 && T <= p.tmax);
+                    }
+                    range = (T > p.tmax) ? p.tmax : T;
+                }
+            } else {
+                // absurd coordinates (|x| >= 1e8 m): the literal reference arithmetic, out of line
+                const double2 r3 = __ldg(rp + 3);
+                const size_t lo = LAYERED ? (size_t)((unsigned long long)__double_as_longlong(r3.x) / p.layer_stride_lean * p.layer_stride) : (size_t)0;
+                const int ti = beam_theta_index(r3.y, i, p.inc, p.theta_dis_f, 1e-6);
+                const double2 sc = __ldg(p.sincos2 + ti);
+                range = march_generic(p.dt + lo, p.orig_x, p.orig_y, p.x_max, p.y_max, p.res, __ldg(p.dt + lo + p.last), p.eps_m,
+                                      p.max_range, (int)p.width, r0.x, r0.y, sc.x, sc.y);
+                n = 1;
+            }
+            if (NOISE) {
+                const unsigned long long tick = p.tick_counter ? *p.tick_counter : 0ull;
+                range = range + p.noise_std * normal_sample(p.noise_seed, tick, (uint64_t)a * (uint64_t)p.B + (uint64_t)i);
+            }
+            const double2 r2 = __ldg(rp + 2);
+            if (range <= r2.x) {
+                const double2 cs2 = __ldg(p.cos_side + i);
+                ttc_exact(range, r2.y, cs2.x, cs2.y, p.ttc_thresh, p.ttc_margin, p.wall_flag + a);
+            }
+            p.out[a * (unsigned)p.B + (unsigned)i] = (float)range;      // M * B < 2^32 (host-checked)
+        }
+        if (COUNT) looks += n;
+        const unsigned mx = __reduce_max_sync(0xffffffffu, n);
+        if (lane == 0) mq.cost[it] = mx;
+    }
+    if (COUNT) {
+        const unsigned nsum = __reduce_add_sync(0xffffffffu, looks);
+        if (lane == 0 && nsum) atomicAdd(p.lookup_counter, (unsigned long long)nsum);
+    }
+}
+
+}  // namespace f110

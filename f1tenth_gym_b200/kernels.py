@@ -46,6 +46,17 @@ def vehicle_dynamics_st(x, u, params):
     return f
 
 
+def vehicle_dynamics_ks(x, u, params):
+    """dynamic_models.py:90-121: x[M,5] = (x, y, steer, v, yaw), u[M,2] -> f[M,5]."""
+    x = _dev(x).reshape(-1, 5)
+    u = _dev(u, device=x.device).reshape(-1, 2)
+    p = _params_dev(params, x.device)
+    f = torch.empty_like(x)
+    nat.check(nat.lib().f110_vehicle_dynamics_ks(nat.ptr(x), nat.ptr(u), nat.ptr(p), x.shape[0], nat.ptr(f),
+                                                 _stream_ptr(x.device)))
+    return f
+
+
 def pid(inputs, params):
     """inputs[M,4] = (speed, steer, current_speed, current_steer) -> (accl[M], sv[M])."""
     x = _dev(inputs).reshape(-1, 4)

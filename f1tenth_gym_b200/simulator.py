@@ -42,7 +42,7 @@ class DeviceMap(object):
         self.theta_dis = theta_dis
         sines, cosines = hostmaps.angle_lut(theta_dis)
         # cell-unit copy for the fast path (res = 2^-k: the division is an exact exponent shift)
-        self.dt_cells = self.dt_codes = self.dt_lut = None
+        self.dt_cells = self.dt_codes = self.dt_lut = self.dt_cells_pad = self.dt_codes_pad = None
         if _device_dt is not None:
             self.dt = _device_dt
             if host_map.fast_path:
@@ -55,14 +55,32 @@ class DeviceMap(object):
                 self.dt_cells = torch.from_numpy(cells).to(device)
                 self.dt_codes = torch.from_numpy(codes).to(device)
                 self.dt_lut = torch.from_numpy(lut).to(device)
+                self.dt_codes_pad = self._pad(self.dt_codes)
+        if self.dt_cells is not None:
+            self.dt_cells_pad = self._pad(self.dt_cells)
         self.sines = torch.from_numpy(sines).to(device)
         self.cosines = torch.from_numpy(cosines).to(device)
-        self.sincos = torch.from_numpy(np.ascontiguousarray(np.stack([sines, cosines], axis=1))).to(device)
+        sc = np.ascontiguousarray(np.stack([sines, cosines], axis=1))
+        self.sincos = torch.from_numpy(sc).to(device)
+        self.sincos2 = torch.from_numpy(np.ascontiguousarray(np.concatenate([sc, sc], axis=0))).to(device)
+        # smallest positive DT value (= resolution for an exact EDT): the lean march kernel tests `d != 0` for `d > eps`
+        pos = self.dt[self.dt > 0]
+        dt_min_positive = float(pos.min().item()) if pos.numel() else float('inf')
         self.c = nat.F110Map(host_map.height, host_map.width, host_map.resolution, host_map.orig_x,
                              host_map.orig_y, host_map.orig_c, host_map.orig_s, eps, max_range, theta_dis,
                              host_map.fast_path, host_map.dt_oob, nat.ptr(self.dt), nat.ptr(self.dt_cells),
                              nat.ptr(self.dt_codes), nat.ptr(self.dt_lut), nat.ptr(self.sines), nat.ptr(self.cosines),
-                             nat.ptr(self.sincos), 1)
+                             nat.ptr(self.sincos), nat.ptr(self.dt_cells_pad), nat.ptr(self.dt_codes_pad),
+                             nat.ptr(self.sincos2), dt_min_positive, 1)
+
+    @staticmethod
+    def _pad(t):
+        """[H][W] -> [H+1][W+1] with the extra row / column holding t[-1,-1] (what an off-map lookup reads)."""
+        H, W = t.shape
+        out = torch.empty((H + 1, W + 1), dtype=t.dtype, device=t.device)
+        out[:] = t[-1, -1]
+        out[:H, :W] = t
+        return out.contiguous()
 
     @classmethod
     def stack(cls, maps):
@@ -79,13 +97,17 @@ class DeviceMap(object):
         out.layers = list(maps)
         out.dt = torch.stack([m.dt for m in maps]).contiguous()
         out.dt_cells = torch.stack([m.dt_cells for m in maps]).contiguous() if m0.dt_cells is not None else None
-        out.dt_codes = out.dt_lut = None
+        out.dt_cells_pad = torch.stack([m.dt_cells_pad for m in maps]).contiguous() if m0.dt_cells_pad is not None else None
+        out.dt_codes = out.dt_lut = out.dt_codes_pad = None
         c = nat.F110Map.from_buffer_copy(m0.c)
         c.dt = nat.ptr(out.dt)
         c.dt_cells = nat.ptr(out.dt_cells)
+        c.dt_cells_pad = nat.ptr(out.dt_cells_pad)
         c.dt_codes = None
         c.dt_lut = None
+        c.dt_codes_pad = None
         c.num_layers = len(maps)
+        c.dt_min_positive = min(m.c.dt_min_positive for m in maps)
         out.c = c
         return out
 
@@ -119,7 +141,7 @@ class DeviceBeams(object):
         self.c = nat.F110Beams(num_beams, fov, self.angle_increment,
                                hostmaps.theta_index_increment(num_beams, fov, theta_dis),
                                nat.ptr(self.scan_angles), nat.ptr(self.cosines), nat.ptr(self.side_distances),
-                               nat.ptr(self.cos_side))
+                               nat.ptr(self.cos_side), float(sd.max()))
 
 
 def empty_map_struct():
@@ -195,6 +217,7 @@ class Simulator(object):
         self.march_cost = torch.full((NA * 256,), -1, **i32) if self.march_ipa else None
         self.march_order = torch.zeros((3, items), **i32) if self.march_ipa else None
         self.march_count = torch.zeros((4,), **i32) if self.march_ipa else None
+        self.march_rec = torch.zeros((NA, 8), **f64) if self.march_ipa else None
         self.beams = DeviceBeams(num_beams, fov, params, dev)
         self.map = None
         self._map_struct = empty_map_struct()
@@ -209,7 +232,7 @@ class Simulator(object):
             nat.ptr(self.start_thetas), nat.ptr(self.start_rot), nat.ptr(self.done),
             nat.ptr(self.checkpoint_done), nat.ptr(self.env_arrivals), None, nat.ptr(self.lookup_counter), nat.ptr(self.tick_counter),
             nat.ptr(self.march_cost), nat.ptr(self.march_order), nat.ptr(self.march_count), self.march_ipa,
-            float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
+            nat.ptr(self.march_rec), float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
         self._graph = None
 
     # ------------------------------------------------------------------ configuration

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define F110_ABI_VERSION 1
+#define F110_ABI_VERSION 2
 #define F110_NPARAM 18     /* mu C_Sf C_Sr lf lr h m I s_min s_max sv_min sv_max v_switch a_max v_min v_max width length
                               (key order of the default dict, f110_env.py:130) */
 #define F110_NSTATE 7      /* x y steer v yaw yaw_rate slip   (base_classes.py:97) */
@@ -57,6 +57,14 @@ typedef struct {
     const double *dt_lut;           /* [256] code -> dt_cells value (bit-exact) */
     const double *sines, *cosines;  /* [theta_dis]  sin/cos(linspace(0, 2pi, theta_dis)) (:379-381) */
     const double *sincos;           /* [theta_dis][2] the same values interleaved (sin, cos), or NULL */
+    const double *dt_cells_pad;     /* [(height+1)*(width+1)] dt_cells with one extra row and column that hold dt[-1,-1]/resolution
+                                       (the off-map value): lets the lean march clamp instead of branch; NULL = round-1 kernels */
+    const uint8_t *dt_codes_pad;    /* [(height+1)*(width+1)] rank codes of dt_cells_pad (same code book as dt_lut), or NULL */
+    const double *sincos2;          /* [2*theta_dis][2] the interleaved LUT stored twice back to back (index k and k + theta_dis
+                                       hold the same pair), or NULL: lets the march index it without the wrap branch */
+    double dt_min_positive;         /* smallest value > 0 in dt (= resolution for an exact EDT), or 0 if unknown.  When it
+                                       exceeds eps, `d > eps` (laser_models.py:134) is the same predicate as `d != 0` and the
+                                       lean march kernel (csrc/march_lean.cuh) may be used */
     int32_t num_layers;             /* 0/1: one map.  L > 1: dt and dt_cells hold L stacked [H][W] tables that share size,
                                        resolution and origin (multi-map batches); f110_sim.env_layer picks one per env */
 } f110_map;
@@ -67,6 +75,7 @@ typedef struct {
     double fov, angle_increment, theta_index_increment;
     const double *scan_angles, *cosines, *side_distances;   /* [num_beams] */
     const double *cos_side;         /* [num_beams][2] (cosines[i], side_distances[i]) interleaved, or NULL */
+    double side_max;                /* max(side_distances), or 0 if unknown: bound used by the per-agent iTTC pre-test */
 } f110_beams;
 
 /* Simulator / RaceCar / F110Env state for N envs x A agents, SoA, caller-owned device memory. */
@@ -108,6 +117,9 @@ typedef struct {
     uint32_t *march_order;          /* [3][I]  */
     uint32_t *march_count;          /* [4]     zero-initialised by the caller */
     int32_t march_ipa;
+    double *march_rec;              /* [N*A][8] per-agent record k_dynamics hands to the lean march kernel (scan position in
+                                       cell units, first lookup, fixed-point LUT index, iTTC threshold, map-layer offset;
+                                       csrc/march_lean.cuh), or NULL: round-1 kernels */
     /* scan noise (laser_models.py:429,450-452): N(0, noise_std^2) per beam, added before iTTC; 0 = off */
     double noise_std;
     uint64_t noise_seed;
@@ -144,6 +156,9 @@ int f110_env_post_step(const f110_sim *sim, void *stream);
 /* Benchmark/RL convenience (no reference equivalent; SURVEY.md 8d policy): every env whose ego has
  * collisions != 0 is reset (Simulator.reset + env counters) to start_poses[k], k drawn from a
  * counter-based hash of (seed, tick, env); agent i takes start_poses[(k - pose_gap*i) mod K].
+ * What the caller sees after a tick that ended an episode: done[env] = 1 and collisions / scans of the crash
+ * (the finished episode's last observation), while state, steer FIFO, lap counters, toggles and current_time are
+ * those of the NEW episode (a car at rest on its start pose, time 0); done is recomputed by the next tick.
  * At most 32 agents per env (F110_ERR_INVALID otherwise; stepping itself has no such limit). */
 int f110_autoreset(const f110_sim *sim, const double *start_poses, int32_t num_start, int32_t pose_gap,
                    uint64_t seed, uint64_t tick, void *stream);
@@ -190,6 +205,9 @@ int f110_scan(const f110_map *map, const f110_beams *beams, const double *poses 
               unsigned long long *lookup_counter /* [1] or NULL */, void *stream);
 /* vehicle_dynamics_st (dynamic_models.py:123-176): x [M][7], u [M][2], params [18] -> f [M][7]. */
 int f110_vehicle_dynamics_st(const double *x, const double *u, const double *params, int32_t M, double *f,
+                             void *stream);
+/* vehicle_dynamics_ks (dynamic_models.py:90-121): x [M][5] (x, y, steer, v, yaw), u [M][2], params [18] -> f [M][5]. */
+int f110_vehicle_dynamics_ks(const double *x, const double *u, const double *params, int32_t M, double *f,
                              void *stream);
 /* pid (dynamic_models.py:178-221): in [M][4] = (speed, steer, current_speed, current_steer) -> out [M][2] = (accl, sv). */
 int f110_pid(const double *in, const double *params, int32_t M, double *out, void *stream);

@@ -88,6 +88,25 @@ def test_scans_other_maps(name):
         assert np.array_equal(oracle.get_scan(m, p, 1080, 4.7), ref)
 
 
+@pytest.mark.parametrize('name', ['example_map', 'berlin', 'skirk', 'vegas', 'stata_basement'])
+def test_scans_wide(name):
+    """208 reference scans per map (tests/golden/make_golden_scans_wide.py): on-track, free space, inside walls, hugging the
+    map border from both sides, far outside and absurd coordinates."""
+    k = g('scans_wide_%s.npz' % name)
+    m = oracle.OracleMap.from_yaml(os.path.join(MAPS, name + '.yaml'), '.png')
+    assert k['poses'].shape == (208, 3)
+    for j, p in enumerate(k['poses']):
+        s = oracle.get_scan(m, p, 1080, 4.7)
+        if name == 'example_map':
+            assert np.array_equal(s, k['scan_1080'][j]), j
+        else:
+            assert np.array_equal(s[k['beam_idx'][j]], k['scan_1080_sub'][j]), j
+    if name == 'example_map':
+        for B in (270, 2160):
+            for p, ref in zip(k['poses'][:48], k['scan_%d' % B]):
+                assert np.array_equal(oracle.get_scan(m, p, B, 4.7), ref)
+
+
 @pytest.mark.parametrize('name', ['traj_a1_random', 'traj_a2_random', 'traj_a2_close', 'traj_a3_euler'])
 def test_trajectories(example_map, name):
     k = g(name + '.npz')

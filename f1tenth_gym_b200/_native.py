@@ -26,7 +26,7 @@ class F110Map(C.Structure):
                 ('dt_oob', C.c_double),
                 ('dt', _dp), ('dt_cells', _dp), ('dt_codes', _dp), ('dt_lut', _dp),
                 ('sines', _dp), ('cosines', _dp), ('sincos', _dp),
-                ('dt_cells_pad', _dp), ('dt_codes_pad', _dp), ('sincos2', _dp),
+                ('dt_cells_pad', _dp), ('dt_codes_pad', _dp), ('codes_pitch', C.c_uint32), ('sincos2', _dp),
                 ('dt_min_positive', C.c_double), ('num_layers', C.c_int32)]
 
 
@@ -98,6 +98,7 @@ SIGNATURES = {
 DEBUG_SIGNATURES = {
     'f110_debug_set_variant': (None, [C.c_int]),
     'f110_debug_set_chunk': (None, [C.c_int]),
+    'f110_debug_set_tile_counter': (None, [C.c_void_p]),
 }
 
 _LIB = None

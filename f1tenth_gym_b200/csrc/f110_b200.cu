@@ -19,6 +19,7 @@
 #include "lidar.cuh"
 #include "march.cuh"
 #include "march_lean.cuh"
+#include "march_tile.cuh"
 #include "planner.cuh"
 #include "edt.cuh"
 #include "trackgen.cuh"
@@ -141,6 +142,30 @@ __device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned fi
     }
 }
 
+// Agent-level queue of the tile march kernel (march_tile.cuh): one thread per agent classifies it by the largest
+// per-slice lookup maximum of the previous tick (unknown = very heavy), same three classes, lists in march_order[3][M].
+__device__ __forceinline__ void build_agent_order(const f110_sim &s, unsigned first_block, unsigned agents) {
+    __shared__ unsigned s_cnt[3], s_base[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned a = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
+    int cls = -1;
+    unsigned slot = 0;
+    if (a < agents) {
+        unsigned m = 0;
+        for (int j = 0; j < s.march_ipa; j++) m = max(m, s.march_cost[((size_t)a << 8) + (size_t)j]);     // unknown = 0xFFFFFFFF wins
+        cls = (m >= F110_Q_VERY_HEAVY) ? 0 : (m >= F110_Q_HEAVY) ? 1 : 2;
+        slot = atomicAdd(&s_cnt[cls], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(s.march_count + threadIdx.x, s_cnt[threadIdx.x]) : 0u;
+    __syncthreads();
+    if (cls >= 0) {
+        const unsigned at = s_base[cls] + slot;
+        if (at < agents) s.march_order[(size_t)cls * agents + at] = a;
+    }
+}
+
 // ------------------------------------------------------------------------------------ k_dynamics
 struct FirstLookup {
     const double *__restrict__ cells;    // dt / res (cell units) or dt (metres), or NULL: generic march kernel
@@ -154,13 +179,15 @@ struct FirstLookup {
     double2 *__restrict__ rec;
     double side_max, ttc_margin;
     unsigned long long rec_layer_stride;     // elements between map layers of the table the lean kernel reads
+    int agent_queue;                         // 1: the extra blocks build the agent-level queue of the tile march kernel
 };
 
 __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
                                                   double theta_dis_f, int dyn_blocks, FirstLookup fl) {
     const int NA = s.num_envs * s.num_agents;
     if ((int)blockIdx.x >= dyn_blocks) {     // extra blocks: build the march work queue (block-uniform branch)
-        build_march_order(s, (unsigned)dyn_blocks, (unsigned)NA * (unsigned)s.march_ipa);
+        if (fl.agent_queue) build_agent_order(s, (unsigned)dyn_blocks, (unsigned)NA);
+        else build_march_order(s, (unsigned)dyn_blocks, (unsigned)NA * (unsigned)s.march_ipa);
         return;
     }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,7 +427,7 @@ __device__ __forceinline__ void finalize_agent(const f110_sim &s, const BeamView
 
 // the march work-queue counters are consumed once k_march has run; the next tick's k_dynamics refills them
 __device__ __forceinline__ void end_of_tick_housekeeping(const f110_sim &s) {
-    if (s.march_count) { s.march_count[0] = 0u; s.march_count[1] = 0u; s.march_count[2] = 0u; }
+    if (s.march_count) { s.march_count[0] = 0u; s.march_count[1] = 0u; s.march_count[2] = 0u; s.march_count[3] = 0u; }
 }
 
 // f110_step: warp per agent
@@ -707,7 +734,8 @@ static int check_beams(const f110_beams *b) {
     return F110_OK;
 }
 
-static unsigned long long *g_trace = nullptr;   // debug only: per-block timeline buffer (f110_debug_set_trace)
+static unsigned long long *g_trace = nullptr;
+static unsigned long long *g_tile_counter = nullptr;   // debug only: lookups served from the shared-memory tile   // debug only: per-block timeline buffer (f110_debug_set_trace)
 
 static int num_sms() {
     static int n = 0;
@@ -780,6 +808,55 @@ static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool
     else launch_lean_t<0, true, false, 4>(q, mq, sms * 4u, noise, count, st);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+template <int TILE, int NSLOT>
+static int launch_tile_t(const TileK &t, const f110_map *map, unsigned sms, bool noise, bool count, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cuda_fail(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point");
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = { (cuuint64_t)map->codes_pitch, (cuuint64_t)(map->height + 1) };
+    const cuuint64_t strides[1] = { (cuuint64_t)map->codes_pitch };
+    const cuuint32_t box[2] = { (cuuint32_t)TILE, (cuuint32_t)TILE };
+    const cuuint32_t estr[2] = { 1u, 1u };
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)map->dt_codes_pad, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    const size_t smem = sizeof(TileSmem<TILE, NSLOT>);
+    constexpr int PT = 512;
+    constexpr int MINB = 4;
+    if (count) {
+        CUDA_TRY(cudaFuncSetAttribute(k_march_tile<false, true, TILE, NSLOT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_march_tile<false, true, TILE, NSLOT, PT, MINB><<<sms * MINB, PT, smem, st>>>(t, tm);
+    } else if (noise) {
+        CUDA_TRY(cudaFuncSetAttribute(k_march_tile<true, false, TILE, NSLOT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_march_tile<true, false, TILE, NSLOT, PT, MINB><<<sms * MINB, PT, smem, st>>>(t, tm);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_march_tile<false, false, TILE, NSLOT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_march_tile<false, false, TILE, NSLOT, PT, MINB><<<sms * MINB, PT, smem, st>>>(t, tm);
+    }
+    return F110_OK;
+}
+static int launch_tile(const TileK &t, const f110_map *map, int tile_sz, unsigned sms, bool noise, bool count, cudaStream_t st) {
+    if (tile_sz == 160) return launch_tile_t<160, 2>(t, map, sms, noise, count, st);
+    return launch_tile_t<128, 3>(t, map, sms, noise, count, st);
+}
+
 template <int MINB, bool CELLS>
 static void launch_march(const MarchK &k, dim3 grid, bool coded, bool noise, bool count, cudaStream_t st) {
     if (coded && CELLS) {
@@ -807,6 +884,7 @@ int f110_abi_version(void) { return F110_ABI_VERSION; }
 void f110_debug_set_trace(unsigned long long *buf) { g_trace = buf; }
 /* measurement aid (not in the public header): select the march kernel variant at run time (tools/ab_march.py) */
 void f110_debug_set_variant(int variant) { g_variant = variant < 0 ? 0 : variant; }
+void f110_debug_set_tile_counter(unsigned long long *buf) { g_tile_counter = buf; }
 void f110_debug_set_chunk(int chunk_shift) { g_chunk = (chunk_shift < 0 || chunk_shift > 6) ? 3 : chunk_shift; }
 
 const char *f110_status_string(int status) {
@@ -852,7 +930,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                         (unsigned long long)NA < (1ull << 22) &&
                         map->orig_c == 1.0 && map->orig_s == 0.0 && map->sincos && beams->cos_side && variant != 13;
     const int dyn_blocks = (NA + 127) / 128;
-    const int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 128 * F110_ORDER_ITEMS_PER_THREAD - 1) /
+    int order_blocks = queued ? (int)(((long long)NA * sim->march_ipa + 128 * F110_ORDER_ITEMS_PER_THREAD - 1) /
                                          (128 * F110_ORDER_ITEMS_PER_THREAD)) : 0;
     // the lean march kernels need an unrotated map origin and the interleaved tables; cell units additionally a
     // power-of-two resolution (fast_path) and the cell-unit table
@@ -880,6 +958,13 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                       map->dt_min_positive > map->eps && beams->fov > 0.0 && beams->fov < 6.283185307179586 &&
                       beams->theta_index_increment > 0.0 && map->theta_dis < 32768 &&
                       variant != 1 && variant != 6;
+    // the TMA-tile kernel (march_tile.cuh; variants 30 / 31): single cell-unit map with the padded code table
+    const int tile_sz = (variant == 31) ? 160 : 128;
+    const bool tile = lean && (variant == 30 || variant == 31) && map->fast_path && map->dt_cells_pad && map->dt_codes_pad &&
+                      map->dt_lut && !(map->num_layers > 1) && map->codes_pitch >= (unsigned)tile_sz && map->codes_pitch % 16 == 0 &&
+                      map->height + 1 >= tile_sz && (unsigned long long)NA * (unsigned long long)sim->march_ipa < (1ull << 24);
+    if (tile) order_blocks = dyn_blocks;
+    fl.agent_queue = tile ? 1 : 0;
     fl.rec = lean ? reinterpret_cast<double2 *>(sim->march_rec) : nullptr;
     fl.side_max = beams->side_max > 0.0 ? beams->side_max : INFINITY;
     fl.ttc_margin = sim->ttc_thresh * 1.000001;
@@ -947,8 +1032,21 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             q.layer_stride = fl.layer_stride; q.layer_stride_lean = fl.rec_layer_stride;
             q.dt = map->dt; q.orig_x = map->orig_x; q.orig_y = map->orig_y; q.dt_oob_unused = 0.0; q.eps_m = map->eps;
             q.max_range = map->max_range;
-            const bool lcoded = cell_units && !layered && map->dt_codes_pad && map->dt_lut && (variant == 20 || variant == 22);
+            q.codes_pitch = map->codes_pitch;
+            const bool lcoded = cell_units && !layered && map->dt_codes_pad && map->dt_lut && map->codes_pitch > (unsigned)map->width &&
+                                (variant == 20 || variant == 22);
             const bool occ3 = (variant == 21 || variant == 22);
+            if (tile) {
+                TileK t;
+                t.l = q;
+                t.order = sim->march_order; t.count = sim->march_count; t.claim = sim->march_count + 3;
+                t.cost = sim->march_cost; t.agents = (unsigned)NA; t.ipa = (unsigned)sim->march_ipa;
+                t.ipa_magic = (unsigned)(4294967296ull / (unsigned long long)sim->march_ipa) + 1u;
+                t.codes_pitch = map->codes_pitch;
+                t.c_max = (int)map->codes_pitch - tile_sz; t.r_max = map->height + 1 - tile_sz;
+                t.tile_counter = g_tile_counter;
+                if ((rc = launch_tile(t, map, tile_sz, (unsigned)num_sms(), noise, count, st))) return rc;
+            } else
             launch_lean(q, mq, (unsigned)num_sms(), cell_units, lcoded, occ3, layered, noise, count, st);
         } else if (queued) {
             const unsigned blocks = (unsigned)num_sms() * 4u;

@@ -47,6 +47,7 @@ struct LeanK {
     unsigned long long noise_seed;
     unsigned guard32;                       // replay when the fraction (top 32 bits) is within guard32 of an integer
     unsigned width, height, last;           // CELLS: `last` unused, the row stride is width + 1
+    unsigned codes_pitch;                   // row pitch of `codes` (>= width + 1, multiple of 16 for TMA)
     int B;
     // literal fallback for absurd coordinates
     const double *__restrict__ dt;
@@ -159,9 +160,8 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
                             const unsigned c = (unsigned)__double2loint(__dadd_rd(X - p.ox, MAGIC));
                             const unsigned r = (unsigned)__double2loint(__dadd_rd(Y - p.oy, MAGIC));
                             // off-map -> the padding row / column, which holds dt[-1,-1]
-                            const unsigned idx = min(r, p.height) * (p.width + 1u) + min(c, p.width);
-                            if (TABLE == 1) D = s_lut[__ldg(p.codes + idx)];
-                            else D = __ldg(table + idx);
+                            if (TABLE == 1) D = s_lut[__ldg(p.codes + min(r, p.height) * p.codes_pitch + min(c, p.width))];
+                            else D = __ldg(table + min(r, p.height) * (p.width + 1u) + min(c, p.width));
                             T = T + D;
                             n++;
                         } while (__double2hiint(D) != 0 && T <= p.tmax);

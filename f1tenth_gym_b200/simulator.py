@@ -55,7 +55,7 @@ class DeviceMap(object):
                 self.dt_cells = torch.from_numpy(cells).to(device)
                 self.dt_codes = torch.from_numpy(codes).to(device)
                 self.dt_lut = torch.from_numpy(lut).to(device)
-                self.dt_codes_pad = self._pad(self.dt_codes)
+                self.dt_codes_pad = self._pad(self.dt_codes, pitch_multiple=16)
         if self.dt_cells is not None:
             self.dt_cells_pad = self._pad(self.dt_cells)
         self.sines = torch.from_numpy(sines).to(device)
@@ -71,13 +71,16 @@ class DeviceMap(object):
                              host_map.fast_path, host_map.dt_oob, nat.ptr(self.dt), nat.ptr(self.dt_cells),
                              nat.ptr(self.dt_codes), nat.ptr(self.dt_lut), nat.ptr(self.sines), nat.ptr(self.cosines),
                              nat.ptr(self.sincos), nat.ptr(self.dt_cells_pad), nat.ptr(self.dt_codes_pad),
+                             0 if self.dt_codes_pad is None else self.dt_codes_pad.shape[1],
                              nat.ptr(self.sincos2), dt_min_positive, 1)
 
     @staticmethod
-    def _pad(t):
-        """[H][W] -> [H+1][W+1] with the extra row / column holding t[-1,-1] (what an off-map lookup reads)."""
+    def _pad(t, pitch_multiple=1):
+        """[H][W] -> [H+1][W+1 rounded up to pitch_multiple] with the extra row / columns holding t[-1,-1] (what an
+        off-map lookup reads)."""
         H, W = t.shape
-        out = torch.empty((H + 1, W + 1), dtype=t.dtype, device=t.device)
+        Wp = -(-(W + 1) // pitch_multiple) * pitch_multiple
+        out = torch.empty((H + 1, Wp), dtype=t.dtype, device=t.device)
         out[:] = t[-1, -1]
         out[:H, :W] = t
         return out.contiguous()

@@ -59,7 +59,9 @@ typedef struct {
     const double *sincos;           /* [theta_dis][2] the same values interleaved (sin, cos), or NULL */
     const double *dt_cells_pad;     /* [(height+1)*(width+1)] dt_cells with one extra row and column that hold dt[-1,-1]/resolution
                                        (the off-map value): lets the lean march clamp instead of branch; NULL = round-1 kernels */
-    const uint8_t *dt_codes_pad;    /* [(height+1)*(width+1)] rank codes of dt_cells_pad (same code book as dt_lut), or NULL */
+    const uint8_t *dt_codes_pad;    /* [(height+1)][codes_pitch] rank codes of dt_cells_pad (same code book as dt_lut; columns beyond
+                                       width hold the off-map code too), or NULL */
+    uint32_t codes_pitch;           /* row pitch of dt_codes_pad in bytes: >= width+1 and a multiple of 16 (TMA global stride) */
     const double *sincos2;          /* [2*theta_dis][2] the interleaved LUT stored twice back to back (index k and k + theta_dis
                                        hold the same pair), or NULL: lets the march index it without the wrap branch */
     double dt_min_positive;         /* smallest value > 0 in dt (= resolution for an exact EDT), or 0 if unknown.  When it

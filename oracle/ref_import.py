@@ -13,7 +13,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("F110_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """The reference tree when it is mounted (build container), else the copy oracle/make_ref.py left in
+    oracle/_ref/ (git-ignored; travels to the GPU box with the snapshot)."""
+    if "F110_REF" in os.environ:
+        return os.environ["F110_REF"]
+    if os.path.isdir("/root/reference/gym/f110_gym/envs"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REF_ROOT = _default_root()
 
 
 def available():

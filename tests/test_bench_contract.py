@@ -1,5 +1,6 @@
-"""bench.py contract (CPU): the reference arm runs here (it times the oracle port on the host cores) and prints one
-JSON line with the agreed keys; the committed round-1 bench line of the CUDA arm carries every key of the contract."""
+"""bench.py contract (CPU): the reference arm runs here (the unmodified numba reference from oracle/_ref or
+/root/reference, one process per core; the oracle C port beside it) and prints one JSON line with the agreed keys whose
+`config` is key-identical to the CUDA arm's; the committed bench lines of the CUDA arm carry every key of the contract."""
 import json
 import os
 import subprocess
@@ -12,7 +13,7 @@ BASE_KEYS = ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_ste
 
 def test_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '3',
-                          '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          '--warmup', '1'], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -21,8 +22,14 @@ def test_reference_arm_prints_one_json_line():
         assert k in d, k
     assert d['impl'] == 'reference' and d['steps'] == 3 and d['warmup'] >= 3          # W >= 3 is enforced
     assert d['metric'] == json.load(open(os.path.join(ROOT, 'BASELINE.json')))['metric']
-    assert d['config']['workload'] == 'cfg2' and d['higher_is_better'] is True
-    assert d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['config']['workload'] == 'cfg3' and d['higher_is_better'] is True       # BASELINE configs[2] is the default
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d['config'] == bench.config_dict('cfg3', 1)               # the same dict the CUDA arm prints (same_config)
+    c = d['cpu_baseline']
+    from oracle import ref_runner
+    assert d['value'] > 0 and c['cores'] >= 1 and c['port_value'] > 0
+    assert c['kind'] == ('reference' if ref_runner.available() else 'port')
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
 
 

@@ -5,8 +5,9 @@
     k_tail) at the same poses equal to fp32(reference fp64 value) beam for beam, with the oracle's lookup count;
   * the tick path at 270 / 540 / 2160 beams with two agents per env (GJK + opponent ray-cast live), incl. the number
     of DT lookups;
-  * every march kernel variant that can be selected (lean fp64 / lean rank-coded / 48-warp builds / the round-1
-    persistent and coded kernels / block-per-tile / literal) against the oracle;
+  * every march kernel variant that can be selected (lean fp64 / lean rank-coded / 48-warp builds / the TMA-tile
+    kernel with 128- and 160-cell tiles / the round-1 persistent and coded kernels / block-per-tile / literal) against
+    the oracle;
   * 64-beam work items (march_item_beams=64);
   * CUDA replay of tests/golden/traj_a2_params.npz (update_params with another body size on one agent);
   * the reference's kinematic single-track known-answer vector on the GPU (f110_vehicle_dynamics_ks);
@@ -91,7 +92,7 @@ def test_scans_wide_standalone(f110, dev, name):
 
 
 @pytest.mark.parametrize('name,v', [('example_map', 0), ('example_map', 20), ('example_map', 21), ('example_map', 22),
-                                    ('example_map', 1), ('example_map', 6), ('example_map', 7), ('example_map', 13),
+                                    ('example_map', 30), ('example_map', 31), ('example_map', 1), ('example_map', 6), ('example_map', 7), ('example_map', 13),
                                     ('berlin', 0), ('berlin', 1), ('skirk', 0), ('vegas', 0), ('stata_basement', 0)])
 def test_tick_path_at_wide_poses(f110, dev, variant, name, v):
     """The production tick path with a car standing at each golden pose (zero action, zero speed: the pose does not
@@ -164,7 +165,7 @@ def test_tick_path_beam_counts_two_agents(f110, dev, example_map, B):
     assert n_col > 0
 
 
-@pytest.mark.parametrize('v', [0, 20, 21, 22, 1, 6, 7, 9, 13])
+@pytest.mark.parametrize('v', [0, 20, 21, 22, 30, 31, 1, 6, 7, 9, 13])
 def test_march_variants_vs_oracle(f110, dev, example_map, variant, v):
     variant(v)
     _rollout_vs_oracle(f110, dev, example_map, N=12, A=2, B=1080, T=40, gap=23, seed=900 + v)

@@ -750,6 +750,7 @@ static int num_sms() {
 // A/B switch for measurements (profiles/): F110_MARCH_VARIANT = 0 default (persistent queue, fp64 cell table),
 // 6 = rank-coded byte table, 7 = no queue (one block per 64-beam tile), 9 = no queue, 40 registers
 static int g_variant = -1, g_chunk = -1;
+static int g_dyn_pct = 85, g_dyn_ahead = 4;      // dynamic queue tail of k_march_lean<DYN> (variants 40 / 41)
 static int rm_variant() {
     if (g_variant < 0) {
         const char *e = getenv("F110_MARCH_VARIANT");
@@ -791,14 +792,20 @@ static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned bl
     }
 }
 
-template <int TABLE, bool CELLS, bool LAYERED, int MINB>
+template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false>
 static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
-    if (count) k_march_lean<TABLE, false, true, CELLS, LAYERED, 512, MINB><<<blocks, 512, 0, st>>>(q, mq);
-    else if (noise) k_march_lean<TABLE, true, false, CELLS, LAYERED, 512, MINB><<<blocks, 512, 0, st>>>(q, mq);
-    else k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB><<<blocks, 512, 0, st>>>(q, mq);
+    if (count) k_march_lean<TABLE, false, true, CELLS, LAYERED, 512, MINB, DYN><<<blocks, 512, 0, st>>>(q, mq);
+    else if (noise) k_march_lean<TABLE, true, false, CELLS, LAYERED, 512, MINB, DYN><<<blocks, 512, 0, st>>>(q, mq);
+    else k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB, DYN><<<blocks, 512, 0, st>>>(q, mq);
 }
 static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool cells, bool coded, bool occ3, bool layered,
-                        bool noise, bool count, cudaStream_t st) {
+                        bool noise, bool count, bool dyn, cudaStream_t st) {
+    if (dyn && cells && !layered && !coded) {
+        if (occ3) launch_lean_t<0, true, false, 3, true>(q, mq, sms * 3u, noise, count, st);
+        else launch_lean_t<0, true, false, 4, true>(q, mq, sms * 4u, noise, count, st);
+        return;
+    }
+    if (dyn && !cells && !layered) { launch_lean_t<0, false, false, 4, true>(q, mq, sms * 4u, noise, count, st); return; }
     if (!cells && layered) launch_lean_t<0, false, true, 4>(q, mq, sms * 4u, noise, count, st);
     else if (!cells) launch_lean_t<0, false, false, 4>(q, mq, sms * 4u, noise, count, st);
     else if (layered) launch_lean_t<0, true, true, 4>(q, mq, sms * 4u, noise, count, st);
@@ -884,6 +891,10 @@ int f110_abi_version(void) { return F110_ABI_VERSION; }
 void f110_debug_set_trace(unsigned long long *buf) { g_trace = buf; }
 /* measurement aid (not in the public header): select the march kernel variant at run time (tools/ab_march.py) */
 void f110_debug_set_variant(int variant) { g_variant = variant < 0 ? 0 : variant; }
+void f110_debug_set_dyn(int static_pct, int ahead) {
+    g_dyn_pct = static_pct < 0 ? 0 : (static_pct > 100 ? 100 : static_pct);
+    g_dyn_ahead = ahead < 1 ? 1 : (ahead > 8 ? 8 : ahead);
+}
 void f110_debug_set_tile_counter(unsigned long long *buf) { g_tile_counter = buf; }
 void f110_debug_set_chunk(int chunk_shift) { g_chunk = (chunk_shift < 0 || chunk_shift > 6) ? 3 : chunk_shift; }
 
@@ -1007,6 +1018,13 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
             if (g_chunk < 0) { const char *e = getenv("F110_MARCH_CHUNK"); g_chunk = e ? atoi(e) : 3; if (g_chunk < 0 || g_chunk > 6) g_chunk = 3; }
             mq.chunk_shift = (unsigned)g_chunk;
+            mq.claim = sim->march_count + 3;
+            {   // dynamic tail of the queue (k_march_lean<DYN>): g_dyn_pct % of every block's share is dealt statically
+                const unsigned runs = (mq.items + (1u << mq.chunk_shift) - 1u) >> mq.chunk_shift;
+                const unsigned blocks = (unsigned)num_sms() * 4u;
+                mq.dyn_ahead = (unsigned)g_dyn_ahead;
+                mq.static_runs = (unsigned)((unsigned long long)runs * (unsigned)g_dyn_pct / 100ull / blocks);
+            }
         }
         if (lean) {
             LeanK q;
@@ -1035,7 +1053,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             q.codes_pitch = map->codes_pitch;
             const bool lcoded = cell_units && !layered && map->dt_codes_pad && map->dt_lut && map->codes_pitch > (unsigned)map->width &&
                                 (variant == 20 || variant == 22);
-            const bool occ3 = (variant == 21 || variant == 22);
+            const bool occ3 = (variant == 21 || variant == 22 || variant == 41);
             if (tile) {
                 TileK t;
                 t.l = q;
@@ -1047,7 +1065,8 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                 t.tile_counter = g_tile_counter;
                 if ((rc = launch_tile(t, map, tile_sz, (unsigned)num_sms(), noise, count, st))) return rc;
             } else
-            launch_lean(q, mq, (unsigned)num_sms(), cell_units, lcoded, occ3, layered, noise, count, st);
+            launch_lean(q, mq, (unsigned)num_sms(), cell_units, lcoded, occ3, layered, noise, count,
+                        /* dynamic queue tail: */ (variant == 40 || variant == 41) && mq.static_runs >= mq.dyn_ahead, st);
         } else if (queued) {
             const unsigned blocks = (unsigned)num_sms() * 4u;
             if (!cell_units) launch_persistent<512, 1, false>(k, mq, blocks, coded, noise, count, st);

@@ -91,6 +91,9 @@ struct MarchQueue {
     unsigned items;                         // M * ipa
     unsigned ipa;                           // 32-beam slices per agent (<= 256)
     unsigned chunk_shift;                   // a block is dealt 2^chunk_shift consecutive queue entries at a time
+    unsigned *claim;                        // global run counter of the dynamic queue tail (k_march_lean<DYN>), zeroed every tick
+    unsigned static_runs;                   // DYN: runs per block that are dealt statically (>= dyn_ahead)
+    unsigned dyn_ahead;                     // DYN: how many local runs ahead a dynamic run is claimed (1..8)
 };
 
 // One beam: LUT heading, sphere tracing in cell units, optional noise, iTTC predicate, fp32 range out.

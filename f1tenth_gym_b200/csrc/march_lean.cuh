@@ -104,9 +104,20 @@ __device__ __noinline__ double redo_beam_cells(const double *__restrict__ table,
 }
 
 // TABLE: 0 = fp64 table in global memory, 1 = u8 rank codes in global memory + fp64 LUT in shared memory
-template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB>
+// DYN: the first mq.static_runs runs (of 2^chunk_shift consecutive queue entries) of every block are dealt statically,
+// round-robin, as before; the REST of the queue is handed out dynamically from one global counter (mq.claim).  Static
+// dealing gives every block the same number of items but not the same amount of work: ncu showed the SMs busy for only
+// 83 % of the kernel's duration (profiles/r2: sm__cycles_active.avg 106.8 k of 127.8 k elapsed cycles).  Claims are
+// prefetched: the warp that draws the first ticket of local run r claims the run for r + mq.dyn_ahead and publishes it in
+// a shared-memory ring, so a ticket only reads two shared words; the global order of the queue (longest first) is kept.
+// (Handing out the WHOLE queue dynamically loses: 17 k same-address atomics per tick queue up behind each other and
+// the claim is late more often than not -- 80.6 us vs 69.0 us at cfg2, profiles/r2/ab_march.md.)
+#define F110_DYN_RING 16u
+template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB, bool DYN = false>
 __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
+    __shared__ unsigned s_run[DYN ? F110_DYN_RING : 1u], s_seq[DYN ? F110_DYN_RING : 1u];
+    if (DYN && threadIdx.x < F110_DYN_RING) s_seq[threadIdx.x] = 0xFFFFFFFFu;
     __shared__ double s_lut[TABLE == 1 ? 256 : 1];
     if (threadIdx.x == 0) s_next = 0u;
     if (TABLE == 1)
@@ -127,7 +138,33 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
         asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
                      : "+r"(k), "=r"(leader) : "r"(s_next_addr) : "memory");
         k = __shfl_sync(0xffffffffu, k, leader);
-        const unsigned q = (k >> cs) * qstride + qbase + (k & qmask);
+        unsigned q;
+        if (DYN) {
+            const unsigned r = k >> cs;
+            if ((k & qmask) == 0u && lane == leader && r + mq.dyn_ahead >= mq.static_runs) {
+                // first ticket of run r: claim the dynamic run that local run r + dyn_ahead will use
+                const unsigned g = atomicAdd(mq.claim, 1u);
+                const unsigned nb = (r + mq.dyn_ahead) & (F110_DYN_RING - 1u);
+                s_run[nb] = mq.static_runs * gridDim.x + g;
+                __threadfence_block();
+                *(volatile unsigned *)&s_seq[nb] = r + mq.dyn_ahead;
+            }
+            if (r < mq.static_runs) {
+                q = r * qstride + qbase + (k & qmask);
+            } else {
+                const unsigned buf = r & (F110_DYN_RING - 1u);
+                unsigned sq;
+                while ((sq = *(volatile unsigned *)&s_seq[buf]) != r) {
+                    // a ring slot is reused 16 runs (>= 64 tickets) later: a warp cannot fall that far behind between
+                    // drawing its ticket and reading the slot; if it ever did, stop loudly instead of marching wrong items
+                    if (sq != 0xFFFFFFFFu && sq > r) __trap();
+                }
+                __threadfence_block();
+                q = (s_run[buf] << cs) + (k & qmask);
+            }
+        } else {
+            q = (k >> cs) * qstride + qbase + (k & qmask);
+        }
         if (q >= total) break;
         const unsigned it = mq.order[(q < nA) ? q : (q < nAB) ? (mq.items + (q - nA)) : (2u * mq.items + (q - nAB))];
         const unsigned a = it >> 8;

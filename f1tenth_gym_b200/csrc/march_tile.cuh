@@ -95,7 +95,9 @@ __device__ __forceinline__ void tile_refill(const TileK &p, const CUtensorMap *t
     // cell of the scan pose (absurd coordinates hold metres here: the origin is clamped, the tile is simply not used)
     const double fx = floor(r0.x - p.l.ox), fy = floor(r0.y - p.l.oy);
     int cc = (fx > -1e9 && fx < 1e9) ? (int)fx : 0, rr = (fy > -1e9 && fy < 1e9) ? (int)fy : 0;
-    cc = max(0, min(cc - TILE / 2, p.c_max));
+    // TMA: the box start must be 16-byte aligned in the innermost dimension (an unaligned start coordinate faults as an
+    // illegal instruction at the UTMALDG): 1-byte cells -> a multiple of 16 columns; c_max is one (pitch and TILE are)
+    cc = max(0, min(cc - TILE / 2, p.c_max)) & ~15;
     rr = max(0, min(rr - TILE / 2, p.r_max));
     s->agent[slot] = a;
     s->org_c[slot] = cc;

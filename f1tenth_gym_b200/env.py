@@ -49,6 +49,9 @@ class F110Env(object):
                              noise_std=kwargs.get('scan_noise_std', 0.01))
         self.sim.set_map(self.map_path, self.map_ext)
         self.render_obs = None
+        # single-env mode: the whole observation comes back in ONE batch of async copies + one stream sync
+        # (C ABI f110_step_host) instead of a blocking .cpu() per field
+        self._io = None if self.batched else self.sim.make_host_io()
 
     # env-level state lives on the device (f110_env.py:165-189); expose the reference's attribute names
     @property
@@ -96,8 +99,29 @@ class F110Env(object):
         info = {'checkpoint_done': sim.checkpoint_done.bool().cpu().numpy()}
         return o, self.timestep, done, info
 
+    def _step_single(self, action):
+        """Reference-shaped step of ONE env (base_classes.py:594-612 obs dict of per-agent lists): actions go through a
+        pinned buffer, f110_step_host runs step + lap logic and copies scans / state / collisions / done / laps back."""
+        sim, io, A = self.sim, self._io, self.num_agents
+        a = np.asarray(action.cpu() if torch.is_tensor(action) else action, dtype=np.float64).reshape(A, 2)
+        io['actions'].numpy()[:] = a
+        sim.step_host(io)
+        st = io['state'].numpy()                      # [7][A]
+        lap_counts = io['lap_counts'].numpy().copy()
+        o = {'ego_idx': self.ego_idx,
+             'scans': [s for s in io['scans'].numpy().astype(np.float64)],
+             'poses_x': [float(v) for v in st[0]], 'poses_y': [float(v) for v in st[1]],
+             'poses_theta': [float(v) for v in st[4]], 'linear_vels_x': [float(v) for v in st[3]],
+             'linear_vels_y': [0.0] * A, 'ang_vels_z': [float(v) for v in st[5]],
+             'collisions': io['collisions'].numpy().copy(),
+             'lap_times': io['lap_times'].numpy().copy(), 'lap_counts': lap_counts}
+        # toggle_list >= 4 (f110_env.py:243) <=> lap_counts = floor(toggle / 2) >= 2
+        return o, self.timestep, bool(io['done'].numpy()[0]), {'checkpoint_done': lap_counts >= 2}
+
     def step(self, action):
         """f110_env.py:263-304."""
+        if not self.batched:
+            return self._step_single(action)
         obs = self.sim.step(action)
         return self._finish(obs)
 

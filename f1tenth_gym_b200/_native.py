@@ -99,6 +99,8 @@ DEBUG_SIGNATURES = {
     'f110_debug_set_variant': (None, [C.c_int]),
     'f110_debug_set_chunk': (None, [C.c_int]),
     'f110_debug_set_dyn': (None, [C.c_int, C.c_int]),
+    'f110_debug_set_pdl': (None, [C.c_int]),
+    'f110_debug_set_tail': (None, [C.c_int]),
     'f110_debug_set_tile_counter': (None, [C.c_void_p]),
 }
 

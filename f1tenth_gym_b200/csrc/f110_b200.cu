@@ -185,6 +185,7 @@ struct FirstLookup {
 __global__ void __launch_bounds__(128) k_dynamics(f110_sim s, const double *__restrict__ actions, double fov,
                                                   double theta_dis_f, int dyn_blocks, FirstLookup fl) {
     const int NA = s.num_envs * s.num_agents;
+    pdl_launch_dependents();                 // the march kernel may start its launch / prologue now (it waits before reading)
     if ((int)blockIdx.x >= dyn_blocks) {     // extra blocks: build the march work queue (block-uniform branch)
         if (fl.agent_queue) build_agent_order(s, (unsigned)dyn_blocks, (unsigned)NA);
         else build_march_order(s, (unsigned)dyn_blocks, (unsigned)NA * (unsigned)s.march_ipa);
@@ -399,26 +400,46 @@ __device__ __forceinline__ void finalize_agent(const f110_sim &s, const BeamView
                 const double dist = sqrt(ddx * ddx + ddy * ddy);
                 if (dist > 1.25 * half_diag) cone = asin(half_diag / dist) + 0.05;
             }
-            for (int i = lo + lane; i <= hi; i += 32) {
-                const float cur = scan[i];          // issued early: often an L2/DRAM miss (the march just wrote it)
-                double bt = yaw + bv.scan_angles[i];
-                double dl = bt - phi;
-                dl = dl - (2 * M_PI) * rint(dl * (1.0 / (2 * M_PI)));
-                // (the mirrored cone is kept too: get_range's collinear branch, laser_models.py:275-278, has no
-                // direction test, so a beam pointing exactly away along an edge line still reports that edge)
-                const double adl = fabs(dl);
-                if (adl > cone && (M_PI - adl) > cone) continue;
-                double v3x, v3y;
-                sincos(bt + M_PI / 2., &v3y, &v3x);
-                double r = INFINITY;
+            // one beam of the window: cone test, then the four edges (only `min(scan, range)` is needed)
+            auto cast_beams = [&](int i0, int i1) {
+                for (int i = i0 + lane; i <= i1; i += 32) {
+                    const float cur = scan[i];          // issued early: often an L2/DRAM miss (the march just wrote it)
+                    double bt = yaw + bv.scan_angles[i];
+                    double dl = bt - phi;
+                    dl = dl - (2 * M_PI) * rint(dl * (1.0 / (2 * M_PI)));
+                    // (the mirrored cone is kept too: get_range's collinear branch, laser_models.py:275-278, has no
+                    // direction test, so a beam pointing exactly away along an edge line still reports that edge)
+                    const double adl = fabs(dl);
+                    if (adl > cone && (M_PI - adl) > cone) continue;
+                    double v3x, v3y;
+                    sincos(bt + M_PI / 2., &v3y, &v3x);
+                    const double curd = (double)cur;
+                    double r = INFINITY;
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    int e2 = (e + 1) & 3;
-                    double d = get_range(px, py, v3x, v3y, v[2 * e], v[2 * e + 1], v[2 * e2], v[2 * e2 + 1]);
-                    if (d < r) r = d;
+                    for (int e = 0; e < 4; e++) {
+                        int e2 = (e + 1) & 3;
+                        double d = get_range_below(px, py, v3x, v3y, v[2 * e], v[2 * e + 1], v[2 * e2], v[2 * e2 + 1], curd);
+                        if (d < r) r = d;
+                    }
+                    float rf = (float)r;
+                    if (rf < cur) scan[i] = rf;
                 }
-                float rf = (float)r;
-                if (rf < cur) scan[i] = rf;
+            };
+            if (cone < 3.5 && hi - lo >= 96) {
+                // wide window (the opponent straddles the rear cut: ALL beams): only beams whose angle lies within `cone` of
+                // the direction to the opponent, or of the opposite direction, can pass the test above.  Those are the
+                // beams around the centres (phi - yaw) + m pi; visit just these index intervals, with two beams of slack
+                // on both sides -- the exact per-beam test still decides.
+                const double base = phi - yaw, half = bv.fov / 2., inv_inc = 1.0 / bv.angle_increment;
+                for (int m = -3; m <= 5; m++) {
+                    const double c = base + (double)m * M_PI;
+                    const double f0 = (c - cone + half) * inv_inc - 2.0, f1 = (c + cone + half) * inv_inc + 2.0;
+                    if (f1 < (double)lo || f0 > (double)hi) continue;
+                    const int i0 = max(lo, (int)floor(fmax(f0, (double)lo))), i1 = min(hi, (int)ceil(fmin(f1, (double)hi)));
+                    cast_beams(i0, i1);
+                }
+            } else {
+                cast_beams(lo, hi);
             }
             __syncwarp();
         }
@@ -432,6 +453,7 @@ __device__ __forceinline__ void end_of_tick_housekeeping(const f110_sim &s) {
 
 // f110_step: warp per agent
 __global__ void __launch_bounds__(128, 8) k_finalize(f110_sim s, BeamView bv, double max_scan_range) {
+    pdl_wait();
     const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (a >= s.num_envs * s.num_agents) return;
@@ -581,8 +603,10 @@ __global__ void k_autoreset(f110_sim s, AutoResetArgs ar) {
 
 // f110_tick: warp per agent; the warp that finishes an env last (per-env arrival counter) also runs the F110Env
 // lap logic and the auto-reset for that env: k_finalize + k_env_post_step + k_autoreset in one launch
-__global__ void __launch_bounds__(1024, 1) k_tail(f110_sim s, BeamView bv, int env_level, AutoResetArgs ar,
-                                                   double max_scan_range, int envs_per_block) {
+// MAXT / MINB: blocks of up to 4 agent-warps (A <= 4) are compiled without the 64-register cap of a 1024-thread block
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_tail(f110_sim s, BeamView bv, int env_level, AutoResetArgs ar,
+                                                      double max_scan_range, int envs_per_block) {
     // a block owns whole envs (blockDim = 32 * A * envs_per_block, A <= 32): the env-level step only needs what the
     // warps of its own block wrote, so a block barrier orders it -- no device-scope fence, no arrival atomics.  (The
     // first version had every warp execute __threadfence() + atomicAdd on a per-env counter; the fence's L1
@@ -590,6 +614,7 @@ __global__ void __launch_bounds__(1024, 1) k_tail(f110_sim s, BeamView bv, int e
     // kernel's stall samples sat on the fences and 8 % on the scan-angle loads behind them.)
     const int A = s.num_agents;
     const int lane = threadIdx.x & 31;
+    pdl_wait();                              // the march kernel (scans, wall flags) must be complete
     const int env0 = blockIdx.x * envs_per_block;
     const int a = env0 * A + (int)(threadIdx.x >> 5);
     if (a < s.num_envs * A) finalize_agent(s, bv, a, lane, max_scan_range);
@@ -792,11 +817,31 @@ static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned bl
     }
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL) when enabled: the kernel may become resident before
+// its predecessor in the stream has finished and synchronises itself with pdl_wait().
+// measured (profiles/r2/ab_march_5_pdl_tail.jsonl): inside a CUDA graph PDL wins nothing (cfg2 85.9 vs 86.0-88.0 us, cfg3 563-573 vs
+// 560-569 us), so it is off by default and kept as a switch (f110_debug_set_pdl); k_tail is fastest with the 64-register
+// budget (occupancy beats spills: cfg3 560.0 / 565.1 / 569.3 us for 64 / 96 / 128 registers)
+static int g_pdl = 0;
+static int g_tail_minb = 8;
+static thread_local bool g_pdl_this_step = false;     // set by step_impl: PDL only when no events are recorded between the kernels
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false>
 static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
-    if (count) k_march_lean<TABLE, false, true, CELLS, LAYERED, 512, MINB, DYN><<<blocks, 512, 0, st>>>(q, mq);
-    else if (noise) k_march_lean<TABLE, true, false, CELLS, LAYERED, 512, MINB, DYN><<<blocks, 512, 0, st>>>(q, mq);
-    else k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB, DYN><<<blocks, 512, 0, st>>>(q, mq);
+    const bool pdl = g_pdl_this_step;
+    if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
+    else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
+    else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
 }
 static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool cells, bool coded, bool occ3, bool layered,
                         bool noise, bool count, bool dyn, cudaStream_t st) {
@@ -895,6 +940,8 @@ void f110_debug_set_dyn(int static_pct, int ahead) {
     g_dyn_pct = static_pct < 0 ? 0 : (static_pct > 100 ? 100 : static_pct);
     g_dyn_ahead = ahead < 1 ? 1 : (ahead > 8 ? 8 : ahead);
 }
+void f110_debug_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+void f110_debug_set_tail(int minb) { g_tail_minb = minb; }
 void f110_debug_set_tile_counter(unsigned long long *buf) { g_tile_counter = buf; }
 void f110_debug_set_chunk(int chunk_shift) { g_chunk = (chunk_shift < 0 || chunk_shift > 6) ? 3 : chunk_shift; }
 
@@ -932,6 +979,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
     const BeamView bv = make_view(beams);
 
     if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
+    g_pdl_this_step = (ev == nullptr);
     const int variant = rm_variant();
     // work-item width: march_ipa = ceil(B/32) -> one 32-beam slice per item, ceil(B/64) -> two
     const int item_sub = (sim->march_ipa == (beams->num_beams + 31) / 32) ? 1
@@ -1105,10 +1153,21 @@ marched:
         // whole envs per block, ~4 warps per block: A = 1 -> 4 envs, A = 2 -> 2 envs, A >= 4 -> 1 env
         const int epb = sim->num_agents >= 4 ? 1 : 4 / sim->num_agents;
         const int threads = 32 * sim->num_agents * epb;
-        k_tail<<<(sim->num_envs + epb - 1) / epb, threads, 0, st>>>(*sim, bv, tail->env_level, tail->ar, max_scan, epb);
+        const dim3 tgrid((sim->num_envs + epb - 1) / epb);
+        const bool tpdl = g_pdl_this_step && lean;
+        // register budget of the 128-thread flavour (A <= 4): 4 blocks/SM = 128 registers (no spills), 5 = 96, 8 = 64
+        if (threads <= 128 && g_tail_minb == 4)
+            launch_k(k_tail<128, 4>, tgrid, dim3(threads), 0, st, tpdl, *sim, bv, (int)tail->env_level, tail->ar, max_scan, epb);
+        else if (threads <= 128 && g_tail_minb == 5)
+            launch_k(k_tail<128, 5>, tgrid, dim3(threads), 0, st, tpdl, *sim, bv, (int)tail->env_level, tail->ar, max_scan, epb);
+        else if (threads <= 128)
+            launch_k(k_tail<128, 8>, tgrid, dim3(threads), 0, st, tpdl, *sim, bv, (int)tail->env_level, tail->ar, max_scan, epb);
+        else
+            launch_k(k_tail<1024, 1>, dim3((sim->num_envs + epb - 1) / epb), dim3(threads), 0, st, g_pdl_this_step && lean, *sim, bv,
+                     (int)tail->env_level, tail->ar, max_scan, epb);
         LAUNCH_CHECK("k_tail");
     } else {
-        k_finalize<<<(NA * 32 + 127) / 128, 128, 0, st>>>(*sim, bv, max_scan);
+        launch_k(k_finalize, dim3((NA * 32 + 127) / 128), dim3(128), 0, st, g_pdl_this_step && lean, *sim, bv, max_scan);
         LAUNCH_CHECK("k_finalize");
         if (tail && tail->fused) {     // more than 32 agents per env: same semantics with separate launches
             if (tail->env_level) { k_env_post_step<<<(sim->num_envs + 127) / 128, 128, 0, st>>>(*sim); LAUNCH_CHECK("k_env_post_step"); }

@@ -10,6 +10,13 @@
 
 namespace f110 {
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream is still running; it must call pdl_wait() before it touches anything the
+// predecessor writes.  pdl_launch_dependents() lets the NEXT kernel of the stream start its launch early.  Both are no-ops
+// for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct MapView {
     const double *__restrict__ dt;
     const double *__restrict__ dt_cells;   // dt / resolution (cell units); fast path only, else NULL
@@ -175,6 +182,40 @@ __device__ __forceinline__ double get_range(double ox, double oy, double v3x, do
         if (d1 >= 0.0 && d2 >= 0.0 && d2 <= 1.0) distance = d1;
     } else {
         // are_collinear(o, va, vb) :232-247
+        double bax = vax - ox, bay = vay - oy, cax = ox - vbx, cay = oy - vby;
+        if (fabs(cross2(bax, bay, cax, cay)) < 1e-8) {
+            double da = sqrt((vax - ox) * (vax - ox) + (vay - oy) * (vay - oy));
+            double db = sqrt((vbx - ox) * (vbx - ox) + (vby - oy) * (vby - oy));
+            distance = da < db ? da : db;
+        }
+    }
+    return distance;
+}
+
+// get_range for the opponent ray-cast, where the only use of the result is `scan[i] = min(scan[i], range)`: identical
+// outcome, but the two fp64 divisions only run for an edge that can actually shorten the beam.  With d1 = c / denom and
+// d2 = n2 / denom (both IEEE quotients), the reference's test `d1 >= 0 and 0 <= d2 <= 1` fails for certain when
+//   |n2| > |denom| (1 + 1e-12)                      (d2 > 1: rounding cannot bring it back to 1),
+//   n2, denom (or c, denom) have opposite signs and the quotient cannot underflow to -0.0   (d2 < 0, d1 < 0),
+// and an edge with |c| >= cur |denom| (1 + 1e-12) has d1 >= cur: it cannot lower a beam that currently reads `cur`.
+__device__ __forceinline__ double get_range_below(double ox, double oy, double v3x, double v3y, double vax, double vay,
+                                                  double vbx, double vby, double cur) {
+    const double v1x = ox - vax, v1y = oy - vay;
+    const double v2x = vbx - vax, v2y = vby - vay;
+    const double denom = v2x * v3x + v2y * v3y;
+    double distance = INFINITY;
+    if (fabs(denom) > 0.0) {
+        const double c = cross2(v2x, v2y, v1x, v1y);
+        const double n2 = v1x * v3x + v1y * v3y;
+        const double ad = fabs(denom);
+        if (fabs(n2) > ad * (1.0 + 1e-12)) return distance;
+        if (((n2 < 0.0) != (denom < 0.0)) && fabs(n2) > 1e-290 * ad) return distance;
+        if (((c < 0.0) != (denom < 0.0)) && fabs(c) > 1e-290 * ad) return distance;
+        if (fabs(c) >= cur * ad * (1.0 + 1e-12)) return distance;
+        const double d1 = c / denom;
+        const double d2 = n2 / denom;
+        if (d1 >= 0.0 && d2 >= 0.0 && d2 <= 1.0) distance = d1;
+    } else {
         double bax = vax - ox, bay = vay - oy, cax = ox - vbx, cay = oy - vby;
         if (fabs(cross2(bax, bay, cax, cay)) < 1e-8) {
             double da = sqrt((vax - ox) * (vax - ox) + (vay - oy) * (vay - oy));

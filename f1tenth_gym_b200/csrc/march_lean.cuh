@@ -122,6 +122,10 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
     if (threadIdx.x == 0) s_next = 0u;
     if (TABLE == 1)
         for (unsigned t = threadIdx.x; t < 256u; t += PT) s_lut[t] = p.lut[t];
+    // everything above touches only launch constants: under PDL it overlaps the end of k_dynamics.  From here on the
+    // kernel reads what k_dynamics wrote (queue, per-agent records).
+    pdl_wait();
+    pdl_launch_dependents();
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nA = min(mq.count[0], mq.items), nB = min(mq.count[1], mq.items);

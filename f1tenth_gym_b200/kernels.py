@@ -127,7 +127,7 @@ class ScanSimulator2D(object):
         self.beams = DeviceBeams(num_beams, fov, hostmaps.DEFAULT_PARAMS, self.device, theta_dis)
         self.map = None
         self.map_height = None
-        self._calls = 0
+        self._noise_offset = 0      # running element offset into the Philox stream: ranges never overlap across calls
 
     def set_map(self, map_path, map_ext):
         self.map = DeviceMap.from_yaml(map_path, map_ext, self.device, theta_dis=self.theta_dis, eps=self.eps,
@@ -159,8 +159,8 @@ class ScanSimulator2D(object):
             if out_f64:
                 raise ValueError('noise is only applied to the fp32 output')
             nat.check(L.f110_scan_noise(nat.ptr(out), out.numel(), float(std_dev), int(rng) & 0xFFFFFFFFFFFFFFFF,
-                                        self._calls * out.numel(), _stream_ptr(self.device)))
-            self._calls += 1
+                                        self._noise_offset, _stream_ptr(self.device)))
+            self._noise_offset += out.numel()
         return (out, int(cnt.item())) if count_lookups else out
 
     def get_increment(self):

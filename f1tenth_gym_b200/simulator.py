@@ -237,6 +237,7 @@ class Simulator(object):
             nat.ptr(self.march_cost), nat.ptr(self.march_order), nat.ptr(self.march_count), self.march_ipa,
             nat.ptr(self.march_rec), float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
         self._graph = None
+        self._zeros_NA = torch.zeros((N, A), dtype=torch.float64, device=dev)     # obs['linear_vels_y'] (always 0, :606)
 
     # ------------------------------------------------------------------ configuration
     def set_map(self, map_path, map_ext, edt='scipy'):
@@ -383,16 +384,23 @@ class Simulator(object):
                 'scans': self.scans.view(N, A, B),
                 'poses_x': st[0].view(N, A), 'poses_y': st[1].view(N, A), 'poses_theta': st[4].view(N, A),
                 'linear_vels_x': st[3].view(N, A),
-                'linear_vels_y': torch.zeros((N, A), dtype=torch.float64, device=self.device),
+                'linear_vels_y': self._zeros_NA,
                 'ang_vels_z': st[5].view(N, A),
                 'collisions': self.collisions.view(N, A)}
 
     # ------------------------------------------------------------------ throughput paths
     def capture_graph(self, actions, autoreset_poses=None, pose_gap=23, autoreset_seed=12345, env_level=False):
         """Capture one tick (f110_step [+ env_post_step] [+ autoreset]) reading `actions` (a persistent
-        device tensor the caller overwrites between replays) into a CUDA graph."""
+        device tensor the caller overwrites between replays) into a CUDA graph.  The warm-up tick that precedes the
+        capture runs on a snapshot: every simulation buffer (state, FIFO, scans, lap counters, tick counter / noise
+        stream, march queue history) is restored afterwards, so capturing has no side effect on the simulation."""
         assert actions.is_cuda and actions.dtype == torch.float64 and actions.is_contiguous()
         L = nat.lib()
+        names = ('state', 'steer_buf', 'steer_cnt', 'scan_pose', 'agent_poses', 'scans', 'wall_flag', 'collisions',
+                 'collision_idx', 'current_time', 'lap_times', 'lap_counts', 'toggle_list', 'near_starts', 'start_xs',
+                 'start_ys', 'start_thetas', 'start_rot', 'done', 'checkpoint_done', 'tick_counter', 'march_cost',
+                 'march_order', 'march_count', 'march_rec')
+        snapshot = {n: getattr(self, n).clone() for n in names if getattr(self, n, None) is not None}
 
         def tick():
             n = 0 if autoreset_poses is None else autoreset_poses.shape[0]
@@ -404,6 +412,9 @@ class Simulator(object):
         with torch.cuda.stream(side):
             tick()      # warm-up outside capture (module load, first-launch work)
         torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        for n, t in snapshot.items():
+            getattr(self, n).copy_(t)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -396,10 +396,11 @@ def test_graph_and_host_paths_match_eager(f110, dev, example_map):
     io = host.make_host_io()
     abuf = torch.zeros((N * A, 2), dtype=torch.float64, device=dev)
     graph_state0 = [t.clone() for t in (graph.state, graph.steer_buf, graph.steer_cnt)]
+    before = (cpu(graph.state).copy(), cpu(graph.steer_cnt).copy(), int(graph.tick_counter.item()), cpu(graph.current_time).copy())
     graph.capture_graph(abuf, env_level=True)
-    # capture_graph ran one warm-up tick: restore the pre-capture state
-    graph.env_reset(poses)
-    graph.tick_counter.zero_()
+    # capture_graph's warm-up tick runs on a snapshot: no side effect on the simulation
+    assert np.array_equal(cpu(graph.state), before[0]) and np.array_equal(cpu(graph.steer_cnt), before[1])
+    assert int(graph.tick_counter.item()) == before[2] and np.array_equal(cpu(graph.current_time), before[3])
     for t in range(T):
         eager.step(acts[t].view(N, A, 2))
         eager.env_post_step()

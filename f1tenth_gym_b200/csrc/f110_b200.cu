@@ -77,66 +77,79 @@ static BeamView make_view(const f110_beams *b) {
 // extra blocks of k_dynamics (it only reads march_cost, which the reset kernels mark as unknown).
 #define F110_ORDER_ITEMS_PER_THREAD 8
 __device__ __forceinline__ void build_march_order(const f110_sim &s, unsigned first_block, unsigned items) {
-    // (1) these blocks run at the occupancy of the 122-register dynamics path (16 warps/SM), so each thread classifies
-    // eight items with all its loads in flight together; (2) the three class counters are single addresses: one
-    // atomic per warp and class serialises in L2 (52 k same-address atomics at cfg3 = the whole 60 us of the kernel),
-    // so slots are handed out from shared-memory counters and the block claims its ranges with three global atomics.
+    // Round 2 (profiles/r2/dynamics_cfg3_line_hot.txt: the builder was 65 % of k_dynamics' instructions at cfg3 -- 24 ballots
+    // and up to 24 shared atomics per thread, a runtime division per item): a thread owns EIGHT CONSECUTIVE items, so
+    //   * one division per thread (the items after the first step (agent, slice) incrementally),
+    //   * the neighbours of an item are the thread's own registers (only the two ends are extra loads: 10 loads, not 24),
+    //   * the per-class counts of a thread are packed into one word (3 x 10 bits) and ONE warp scan places all of them,
+    //   * a warp touches the three shared counters once, the block the three global ones once,
+    // and a class list is in item order within a block, i.e. consecutive entries are neighbouring slices of one agent.
     __shared__ unsigned s_cnt[3], s_base[3];
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned warp = (((blockIdx.x - first_block) * blockDim.x + threadIdx.x) >> 5);
     const unsigned ipa = (unsigned)s.march_ipa;
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+    const unsigned t = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
+    const unsigned w0 = t * F110_ORDER_ITEMS_PER_THREAD;
+    unsigned packed[F110_ORDER_ITEMS_PER_THREAD], c[F110_ORDER_ITEMS_PER_THREAD + 2];
     int cls[F110_ORDER_ITEMS_PER_THREAD];
-    unsigned packed[F110_ORDER_ITEMS_PER_THREAD], slot[F110_ORDER_ITEMS_PER_THREAD];
-    {
-        unsigned c[F110_ORDER_ITEMS_PER_THREAD], cl[F110_ORDER_ITEMS_PER_THREAD], cr[F110_ORDER_ITEMS_PER_THREAD];
-#pragma unroll
-        for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
-            const unsigned w = (warp * F110_ORDER_ITEMS_PER_THREAD + (unsigned)k) * 32u + lane;
-            cls[k] = -1; packed[k] = 0; slot[k] = 0; c[k] = cl[k] = cr[k] = F110_Q_UNKNOWN;
-            if (w < items) {
-                const unsigned a = w / ipa, j = w - a * ipa;
-                packed[k] = (a << 8) | j;
-                c[k] = s.march_cost[packed[k]];
-                if (j > 0) cl[k] = s.march_cost[packed[k] - 1];
-                if (j + 1 < ipa) cr[k] = s.march_cost[packed[k] + 1];
-                cls[k] = 0;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
-            if (cls[k] == 0) {
-                unsigned m = c[k];
-                if (c[k] != F110_Q_UNKNOWN) {
-                    if (cl[k] != F110_Q_UNKNOWN) m = max(m, cl[k]);
-                    if (cr[k] != F110_Q_UNKNOWN) m = max(m, cr[k]);
-                }
-                cls[k] = (c[k] == F110_Q_UNKNOWN || c[k] >= F110_Q_VERY_HEAVY) ? 0 : (m >= F110_Q_HEAVY) ? 1 : 2;
-            }
-        }
-    }
-    __syncthreads();
+    unsigned a = 0, j = 0;
+    if (w0 < items) { a = w0 / ipa; j = w0 - a * ipa; }
+    // c[0] = left neighbour of the first item, c[1..8] = the items, c[9] = right neighbour of the last one
+    c[0] = (w0 < items && j > 0) ? s.march_cost[((a << 8) | j) - 1u] : F110_Q_UNKNOWN;
+    unsigned aa = a, jj = j;
 #pragma unroll
     for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
+        const bool live = w0 + (unsigned)k < items;
+        packed[k] = (aa << 8) | jj;
+        c[k + 1] = live ? s.march_cost[packed[k]] : F110_Q_UNKNOWN;
+        cls[k] = live ? 0 : -1;
+        if (++jj == ipa) { jj = 0; aa++; }
+    }
+    {
+        const unsigned wl = w0 + F110_ORDER_ITEMS_PER_THREAD;      // the item after this thread's last one
+        c[F110_ORDER_ITEMS_PER_THREAD + 1] = (wl < items && jj > 0) ? s.march_cost[(aa << 8) | jj] : F110_Q_UNKNOWN;
+    }
+    unsigned mine = 0u;                                             // per-class counts, 10 bits each
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const unsigned msk = __ballot_sync(0xffffffffu, cls[k] == q);
-            if (msk) {
-                unsigned base = 0;
-                const int leader = __ffs(msk) - 1;
-                if ((int)lane == leader) base = atomicAdd(&s_cnt[q], (unsigned)__popc(msk));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (cls[k] == q) slot[k] = base + (unsigned)__popc(msk & ((1u << lane) - 1u));
+    for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
+        if (cls[k] == 0) {
+            const unsigned sj = packed[k] & 255u;
+            unsigned m = c[k + 1];
+            if (m != F110_Q_UNKNOWN) {
+                // neighbours only inside the same agent: slice 0 has no left one, slice ipa-1 no right one
+                if (sj > 0 && c[k] != F110_Q_UNKNOWN) m = max(m, c[k]);
+                if (sj + 1 < ipa && c[k + 2] != F110_Q_UNKNOWN) m = max(m, c[k + 2]);
             }
+            cls[k] = (c[k + 1] == F110_Q_UNKNOWN || c[k + 1] >= F110_Q_VERY_HEAVY) ? 0 : (m >= F110_Q_HEAVY) ? 1 : 2;
+            mine += 1u << (10 * cls[k]);
         }
     }
+    // exclusive warp scan of the packed counts (a warp holds at most 256 items per class: 9 bits)
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    const unsigned excl = incl - mine;
+    const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+    __syncthreads();                                                // s_cnt zeroed
+    unsigned wbase = 0u;                                            // lanes 0..2 fetch the warp's base of class `lane`
+    if (lane < 3u) {
+        const unsigned n = (wtot >> (10 * lane)) & 1023u;
+        wbase = n ? atomicAdd(&s_cnt[lane], n) : 0u;
+    }
+    const unsigned b0 = __shfl_sync(0xffffffffu, wbase, 0), b1 = __shfl_sync(0xffffffffu, wbase, 1),
+                   b2 = __shfl_sync(0xffffffffu, wbase, 2);
     __syncthreads();
     if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(s.march_count + threadIdx.x, s_cnt[threadIdx.x]) : 0u;
     __syncthreads();
+    unsigned pos[3] = { s_base[0] + b0 + (excl & 1023u), s_base[1] + b1 + ((excl >> 10) & 1023u),
+                        s_base[2] + b2 + ((excl >> 20) & 1023u) };
 #pragma unroll
     for (int k = 0; k < F110_ORDER_ITEMS_PER_THREAD; k++) {
         if (cls[k] >= 0) {
-            const unsigned at = s_base[cls[k]] + slot[k];
+            const unsigned at = (cls[k] == 0) ? pos[0]++ : (cls[k] == 1) ? pos[1]++ : pos[2]++;
             if (at < items) s.march_order[(size_t)cls[k] * items + at] = packed[k];
         }
     }

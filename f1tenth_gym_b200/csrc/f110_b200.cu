@@ -407,8 +407,11 @@ __device__ __forceinline__ void finalize_agent(const f110_sim &s, const BeamView
             // (laser_models.py:310-315 takes min/max of the four nearest-beam indices).  A ray can only meet an
             // edge if it points into the cone that contains the opponent's bounding circle, so beams outside
             // that cone (+0.05 rad of slack) would get four `inf` ranges and leave the scan unchanged: skip them.
-            double cone = 4.0;      // > pi: no filtering when the ego is inside / next to the bounding circle
-            {
+            // The cone (an asin and a sqrt) is only worth computing for a WIDE window; a narrow window (opponent in front)
+            // consists of beams that point at the opponent anyway, so it runs unfiltered (cone = 4 > pi).
+            double cone = 4.0;      // > pi: no filtering (also when the ego is inside / next to the bounding circle)
+            const bool wide = hi - lo >= 96;
+            if (wide) {
                 const double ddx = pb[0] - px, ddy = pb[1] - py;
                 const double dist = sqrt(ddx * ddx + ddy * ddy);
                 if (dist > 1.25 * half_diag) cone = asin(half_diag / dist) + 0.05;
@@ -438,13 +441,16 @@ __device__ __forceinline__ void finalize_agent(const f110_sim &s, const BeamView
                     if (rf < cur) scan[i] = rf;
                 }
             };
-            if (cone < 3.5 && hi - lo >= 96) {
+            if (cone < 3.5 && wide) {
                 // wide window (the opponent straddles the rear cut: ALL beams): only beams whose angle lies within `cone` of
                 // the direction to the opponent, or of the opposite direction, can pass the test above.  Those are the
                 // beams around the centres (phi - yaw) + m pi; visit just these index intervals, with two beams of slack
                 // on both sides -- the exact per-beam test still decides.
                 const double base = phi - yaw, half = bv.fov / 2., inv_inc = 1.0 / bv.angle_increment;
-                for (int m = -3; m <= 5; m++) {
+                // centres base + m pi that can reach the beam range [-half, half] (+- cone and slack): usually 1-3 of them
+                const int m0 = max(-3, (int)floor((-half - cone - 0.02 - base) * (1.0 / M_PI))),
+                          m1 = min(5, (int)ceil((half + cone + 0.02 - base) * (1.0 / M_PI)));
+                for (int m = m0; m <= m1; m++) {
                     const double c = base + (double)m * M_PI;
                     const double f0 = (c - cone + half) * inv_inc - 2.0, f1 = (c + cone + half) * inv_inc + 2.0;
                     if (f1 < (double)lo || f0 > (double)hi) continue;
@@ -852,6 +858,10 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false>
 static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
     const bool pdl = g_pdl_this_step;
+    if (rm_variant() == 50) {      // A/B: ask for the largest L1 explicitly (the kernel uses 16 bytes of shared memory)
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB, DYN>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); done = true; }
+    }
     if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
     else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
     else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);

@@ -94,20 +94,28 @@ def ncu_traffic(workload):
         return None
 
 
+def pci_bus_id(gpu_index):
+    """PCI bus id ('0000:1b:00.0') of CUDA device `gpu_index` (honours CUDA_VISIBLE_DEVICES, unlike an NVML index)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(gpu_index)
+        return '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        return bus[4:] if len(bus.split(':')[0]) == 8 else bus      # NVML prints an 8-digit domain, sysfs a 4-digit one
+
+
 def numa_bind(gpu_index):
     """Pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned allocation: cudaHostAlloc places the pages
     where the calling thread runs, and a D2H into the far socket's memory costs a third of the PCIe rate (round 1,
     8 GPUs: 52 -> 38 GB/s per GPU)."""
     info = {'bound': False}
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
-        if len(bus.split(':')[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
-            bus = bus[4:]
+        bus = pci_bus_id(gpu_index)
+        info['pci'] = bus
         with open('/sys/bus/pci/devices/%s/numa_node' % bus) as f:
             node = int(f.read().strip())
         info['gpu_numa_node'] = node
@@ -140,7 +148,10 @@ class ClockSampler(threading.Thread):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id(index).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
             self.ok = True
         except Exception:
@@ -292,7 +303,7 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------- GPU side
 def measure_workload(name, K, W, world, rank, dev, dmap, Ke, prof_ticks, f110, torch, dist, reduce_max_scalar,
-                     sampler_index=None):
+                     sampler_index=None, packed=False):
     """One workload on this rank's GPU -> dict(value, ms_per_step, e2e, roofline, clocks, ...) (whole-job figures)."""
     w = WORKLOADS[name]
     N, A, B = w['num_envs'], w['num_agents'], w['num_beams']
@@ -414,9 +425,30 @@ def measure_workload(name, K, W, world, rank, dev, dmap, Ke, prof_ticks, f110, t
            'api': 'Simulator.step_host_async -> C ABI f110_step_host_async: per tick pinned H2D of the actions, tick, '
                   'D2H of scans+state+collisions+done+laps into pinned host buffers (2-deep pipeline, the host waits for '
                   'obs t-2 before issuing tick t)'}
+    # ---- the same pipeline with the OPT-IN narrow scan block (24-bit fixed point, 3 bytes per beam): reported beside the
+    # fp32 figure above, never instead of it
+    e2e_u24 = None
+    if packed:
+        del sets
+        sets = sim.make_host_pipeline(depth=2, packed_scans=True)
+        for io in sets:
+            io['_actions_np'] = io['actions'].numpy()
+        e2e_loop(6)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e2e_loop(Ke)
+        torch.cuda.synchronize(dev)
+        p_s = reduce_max_scalar(time.perf_counter() - t0, dev)
+        d2h_p = NA * B * 3 + NA * 7 * 8 + NA * 8 + N + 2 * NA * 8
+        e2e_u24 = {'value': Ke * NA * world / p_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_p,
+                   'steps': Ke, 'ms_per_step': 1e3 * p_s / Ke, 'd2h_gbs_per_gpu': d2h_p / (p_s / Ke) / 1e9,
+                   'what': 'opt-in narrow observation: ranges as 24-bit fixed point (2^-19 m steps, |error| <= 9.6e-7 m), packed on the '
+                           'device by f110_pack_scans_u24 inside f110_step_host_async; everything else as in e2e'}
     del sets, sim, flush
     torch.cuda.empty_cache()
-    return {'value': value, 'ms_per_step': dev_ms_total / K, 'steps': K, 'warmup': W, 'e2e': e2e, 'roofline': roofline,
+    return {'value': value, 'e2e_packed_u24': e2e_u24, 'ms_per_step': dev_ms_total / K, 'steps': K, 'warmup': W, 'e2e': e2e, 'roofline': roofline,
             'clocks': clocks, 'wall_ms_per_step_incl_flush': 1e3 * wall / K, 'num_envs_per_gpu': N, 'num_agents': A,
             'num_beams': B,
             'step_ms_percentiles': {'p5': float(np.percentile(step_ms, 5)), 'p50': float(np.percentile(step_ms, 50)),
@@ -427,9 +459,9 @@ def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    numa = numa_bind(local_rank)            # before torch allocates anything pinned
     import torch
     import torch.distributed as dist
+    numa = numa_bind(local_rank)            # before anything pinned is allocated (make_host_pipeline)
     import f1tenth_gym_b200 as f110
     from f1tenth_gym_b200.distributed import reduce_max_scalar, all_gather_obs
 
@@ -456,22 +488,24 @@ def run_b200(args):
     dmap = f110.DeviceMap.from_yaml(f110.maps.resolve_map_path('example_map'), '.png', dev)
     common = dict(world=world, rank=rank, dev=dev, dmap=dmap, f110=f110, torch=torch, dist=dist,
                   reduce_max_scalar=reduce_max_scalar)
-    main = measure_workload(args.workload, K, W, Ke=min(K, 200), prof_ticks=20, sampler_index=local_rank, **common)
+    main = measure_workload(args.workload, K, W, Ke=min(K, 200), prof_ticks=20, sampler_index=local_rank, packed=True, **common)
 
     # optional NCCL observation all-gather for a single-process trainer, timed OFF the step path
     gather = None
     if world > 1:
         w = WORKLOADS[args.workload]
         shard = torch.zeros((w['num_envs'] * w['num_agents'], w['num_beams']), dtype=torch.float32, device=dev)
+        sizes = [shard.shape[0]] * world              # equal shards: one all_gather_into_tensor, no size exchange
+        full = torch.empty((shard.shape[0] * world, shard.shape[1]), dtype=shard.dtype, device=dev)
         for _ in range(3):
-            full = all_gather_obs(shard)
+            all_gather_obs(shard, sizes=sizes, out=full)
         torch.cuda.synchronize(dev)
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         e0.record()
         for _ in range(reps):
-            full = all_gather_obs(shard)
+            all_gather_obs(shard, sizes=sizes, out=full)
         e1.record()
         torch.cuda.synchronize(dev)
         ms = reduce_max_scalar(e0.elapsed_time(e1) / reps, dev)
@@ -514,7 +548,7 @@ def run_b200(args):
                                 'l2': 'flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)',
                                 'timing': 'sum of per-step CUDA-event times on the launch stream, max over ranks',
                                 'numa': numa},
-                'clocks': main['clocks'], 'e2e': main['e2e'],
+                'clocks': main['clocks'], 'e2e': main['e2e'], 'e2e_packed_u24': main['e2e_packed_u24'],
                 # per tick: k_dynamics (+ march queue build), k_march_lean, k_tail (finalize + lap logic + auto-reset)
                 'gpu_launches': 3 * K, 'roofline': main['roofline'], 'cpu_baseline': cpu,
                 'wall_ms_per_step_incl_flush': main['wall_ms_per_step_incl_flush'],

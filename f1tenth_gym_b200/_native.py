@@ -55,7 +55,7 @@ class F110Sim(C.Structure):
 
 class F110HostObs(C.Structure):
     _fields_ = [('scans', _dp), ('state', _dp), ('collisions', _dp), ('done', _dp),
-                ('lap_times', _dp), ('lap_counts', _dp)]
+                ('lap_times', _dp), ('lap_counts', _dp), ('scans_u24', _dp)]
 
 
 # name -> (restype, argtypes); this table is also what tests use to check that every symbol declared
@@ -92,6 +92,7 @@ SIGNATURES = {
     'f110_edt': (C.c_int, [_dp, C.c_int32, C.c_int32, C.c_double, _dp, _dp, _dp, _dp]),
     'f110_rasterize_track': (C.c_int, [_dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     'f110_scan_noise': (C.c_int, [_dp, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, _dp]),
+    'f110_pack_scans_u24': (C.c_int, [_dp, C.c_int64, _dp, _dp]),
 }
 
 # measurement / test aids exported by the library but not part of the public header

@@ -751,6 +751,31 @@ __global__ void k_ray_cast(BeamView bv, const double *__restrict__ poses, const 
     }
 }
 
+// four ranges -> three 32-bit words (12 bytes): 24-bit fixed point with 2^-19 m steps
+__global__ void k_pack_u24(const float *__restrict__ scans, long long count, uint8_t *__restrict__ out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i0 = g * 4;
+    if (i0 >= count) return;
+    unsigned q[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float r = (i0 + k < count) ? scans[i0 + k] : 0.0f;
+        const float v = fminf(fmaxf(r, 0.0f) * 524288.0f, 16777215.0f);      // 2^19; exact scaling, then round to nearest
+        q[k] = (unsigned)__float2uint_rn(v);
+    }
+    if (i0 + 4 <= count && ((i0 * 3) & 3) == 0) {
+        unsigned *o = reinterpret_cast<unsigned *>(out + i0 * 3);
+        o[0] = q[0] | (q[1] << 24);
+        o[1] = (q[1] >> 8) | (q[2] << 16);
+        o[2] = (q[2] >> 16) | (q[3] << 8);
+    } else {
+        for (int k = 0; k < 4 && i0 + k < count; k++) {
+            uint8_t *o = out + (i0 + k) * 3;
+            o[0] = (uint8_t)q[k]; o[1] = (uint8_t)(q[k] >> 8); o[2] = (uint8_t)(q[k] >> 16);
+        }
+    }
+}
+
 __global__ void k_scan_noise(float *__restrict__ scans, long long count, double std_dev, uint64_t seed,
                              uint64_t offset) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -855,19 +880,18 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false>
+template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false, int PT = 512>
 static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
     const bool pdl = g_pdl_this_step;
-    if (rm_variant() == 50) {      // A/B: ask for the largest L1 explicitly (the kernel uses 16 bytes of shared memory)
-        static bool done = false;
-        if (!done) { cudaFuncSetAttribute(k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB, DYN>, cudaFuncAttributePreferredSharedMemoryCarveout, 0); done = true; }
-    }
-    if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
-    else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
-    else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, 512, MINB, DYN>, dim3(blocks), dim3(512), 0, st, pdl, q, mq);
+    if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, PT, MINB, DYN>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, PT, MINB, DYN>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, PT, MINB, DYN>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
 }
 static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool cells, bool coded, bool occ3, bool layered,
                         bool noise, bool count, bool dyn, cudaStream_t st) {
+    // A/B of the block shape at the same 64 warps/SM: 2 x 1024 threads (variant 60), 8 x 256 (variant 61)
+    if (cells && !layered && !coded && rm_variant() == 60) { launch_lean_t<0, true, false, 2, false, 1024>(q, mq, sms * 2u, noise, count, st); return; }
+    if (cells && !layered && !coded && rm_variant() == 61) { launch_lean_t<0, true, false, 8, false, 256>(q, mq, sms * 8u, noise, count, st); return; }
     if (dyn && cells && !layered && !coded) {
         if (occ3) launch_lean_t<0, true, false, 3, true>(q, mq, sms * 3u, noise, count, st);
         else launch_lean_t<0, true, false, 4, true>(q, mq, sms * 4u, noise, count, st);
@@ -1350,11 +1374,16 @@ int f110_step_host_async(const f110_sim *sim, const f110_map *map, const f110_be
     for (int i = 0; i < 6; i++)
         if (parts[i].dst_dev && parts[i].dst_host && parts[i].src)
             CUDA_TRY(cudaMemcpyAsync(parts[i].dst_dev, parts[i].src, parts[i].bytes, cudaMemcpyDeviceToDevice, cs));
+    // narrow scan block: the snapshot IS the packing (3 bytes per beam cross PCIe instead of 4)
+    const bool packed = !stage->scans && !out->scans && stage->scans_u24 && out->scans_u24;
+    if (packed && (rc = f110_pack_scans_u24(sim->scans, (int64_t)(NA * beams->num_beams), stage->scans_u24, cs))) return rc;
     CUDA_TRY(cudaEventRecord(e_tick, cs));
     CUDA_TRY(cudaStreamWaitEvent(ps, e_tick, 0));
     for (int i = 0; i < 6; i++)
         if (parts[i].dst_dev && parts[i].dst_host && parts[i].src)
             CUDA_TRY(cudaMemcpyAsync(parts[i].dst_host, parts[i].dst_dev, parts[i].bytes, cudaMemcpyDeviceToHost, ps));
+    if (packed)
+        CUDA_TRY(cudaMemcpyAsync(out->scans_u24, stage->scans_u24, NA * beams->num_beams * 3, cudaMemcpyDeviceToHost, ps));
     CUDA_TRY(cudaEventRecord(e_copy, ps));
     return F110_OK;
 }
@@ -1493,6 +1522,14 @@ int f110_rasterize_track(const double *segments, int32_t num_segments, double wa
     k_rasterize_track<<<grid, block, smem, (cudaStream_t)stream>>>(segments, num_segments, wall_inner * wall_inner,
                                                                     wall_outer * wall_outer, height, width, occupied, dist2_out);
     LAUNCH_CHECK("k_rasterize_track");
+    return F110_OK;
+}
+
+int f110_pack_scans_u24(const float *scans, int64_t count, uint8_t *out, void *stream) {
+    if (!scans || !out || count <= 0) return F110_ERR_INVALID;
+    const long long groups = (count + 3) / 4;
+    k_pack_u24<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(scans, (long long)count, out);
+    LAUNCH_CHECK("k_pack_u24");
     return F110_OK;
 }
 

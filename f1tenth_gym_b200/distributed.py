@@ -19,17 +19,27 @@ def env_seeds(base_seed, lo, hi):
     return [base_seed + e for e in range(lo, hi)]
 
 
-def all_gather_obs(local, group=None):
+def all_gather_obs(local, group=None, sizes=None, out=None):
     """Concatenate per-rank observation shards along dim 0 on every rank.  Shards may have different
-    leading sizes (uneven env split): sizes are exchanged first, shards padded to the max."""
+    leading sizes (uneven env split): sizes are exchanged first, shards padded to the max.
+    sizes: the leading size of every rank's shard if the caller already knows them (skips the size exchange and its
+    host sync).  When all shards are equal the gather writes straight into one output tensor (`out`, optional,
+    [sum(sizes), ...]) with a single NCCL all_gather over NVLink -- no padding, no concatenation copy."""
     if not dist.is_available() or not dist.is_initialized():
         return local
     world = dist.get_world_size(group)
-    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        got = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(got, n_local, group=group)
+        sizes = [int(s.item()) for s in got]
+    sizes = [int(x) for x in sizes]
     n_max = max(sizes)
+    if min(sizes) == n_max and hasattr(dist, 'all_gather_into_tensor'):
+        if out is None:
+            out = torch.empty((n_max * world,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = local
     if local.shape[0] < n_max:
         pad = torch.cat([local, local.new_zeros((n_max - local.shape[0],) + tuple(local.shape[1:]))], dim=0)

@@ -426,20 +426,31 @@ class Simulator(object):
     def replay(self):
         self._graph.replay()
 
-    def make_host_io(self, with_scans=True):
-        """Pinned host buffers for step_host()."""
+    def make_host_io(self, with_scans=True, packed_scans=False):
+        """Pinned host buffers for step_host() / step_host_async().  packed_scans=True (async path only): the scan block
+        crosses PCIe as 24-bit fixed point (io['scans_u24'] uint8 [NA, B, 3]; decode with unpack_scans_u24) instead of fp32."""
         N, A, B = self.num_envs, self.num_agents, self.num_beams
         NA = N * A
+        if packed_scans:
+            with_scans = False
         io = {'actions': torch.zeros((NA, 2), dtype=torch.float64).pin_memory(),
               'scans': torch.zeros((NA, B), dtype=torch.float32).pin_memory() if with_scans else None,
+              'scans_u24': torch.zeros((NA, B, 3), dtype=torch.uint8).pin_memory() if packed_scans else None,
               'state': torch.zeros((7, NA), dtype=torch.float64).pin_memory(),
               'collisions': torch.zeros((NA,), dtype=torch.float64).pin_memory(),
               'done': torch.zeros((N,), dtype=torch.uint8).pin_memory(),
               'lap_times': torch.zeros((NA,), dtype=torch.float64).pin_memory(),
               'lap_counts': torch.zeros((NA,), dtype=torch.float64).pin_memory()}
         io['_struct'] = nat.F110HostObs(nat.ptr(io['scans']), nat.ptr(io['state']), nat.ptr(io['collisions']),
-                                        nat.ptr(io['done']), nat.ptr(io['lap_times']), nat.ptr(io['lap_counts']))
+                                        nat.ptr(io['done']), nat.ptr(io['lap_times']), nat.ptr(io['lap_counts']),
+                                        nat.ptr(io['scans_u24']))
         return io
+
+    @staticmethod
+    def unpack_scans_u24(buf):
+        """uint8 [..., 3] (io['scans_u24']) -> float32 ranges: (b0 | b1 << 8 | b2 << 16) * 2^-19 m."""
+        b = (buf.numpy() if torch.is_tensor(buf) else np.asarray(buf)).astype(np.uint32)
+        return ((b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16)).astype(np.float32) * np.float32(2.0 ** -19))
 
     def step_host(self, io):
         """One tick through HOST buffers (C ABI f110_step_host): H2D actions, step, env_post_step,
@@ -449,7 +460,7 @@ class Simulator(object):
                                            C.byref(io['_struct']), _stream_ptr(self.device)))
         return io
 
-    def make_host_pipeline(self, depth=2, with_scans=True):
+    def make_host_pipeline(self, depth=2, with_scans=True, packed_scans=False):
         """`depth` independent sets of (pinned host obs, device staging, events, actions scratch) for
         step_host_async(); one shared copy stream."""
         N, A, B = self.num_envs, self.num_agents, self.num_beams
@@ -457,9 +468,12 @@ class Simulator(object):
         dev = self.device
         copy_stream = torch.cuda.Stream(dev)
         sets = []
+        if packed_scans:
+            with_scans = False
         for _ in range(depth):
-            io = self.make_host_io(with_scans)
+            io = self.make_host_io(with_scans, packed_scans)
             st = {'scans': torch.zeros((NA, B), dtype=torch.float32, device=dev) if with_scans else None,
+                  'scans_u24': torch.zeros((NA, B, 3), dtype=torch.uint8, device=dev) if packed_scans else None,
                   'state': torch.zeros((7, NA), dtype=torch.float64, device=dev),
                   'collisions': torch.zeros((NA,), dtype=torch.float64, device=dev),
                   'done': torch.zeros((N,), dtype=torch.uint8, device=dev),
@@ -467,7 +481,8 @@ class Simulator(object):
                   'lap_counts': torch.zeros((NA,), dtype=torch.float64, device=dev)}
             io['_stage'] = st
             io['_stage_struct'] = nat.F110HostObs(nat.ptr(st['scans']), nat.ptr(st['state']), nat.ptr(st['collisions']),
-                                                  nat.ptr(st['done']), nat.ptr(st['lap_times']), nat.ptr(st['lap_counts']))
+                                                  nat.ptr(st['done']), nat.ptr(st['lap_times']), nat.ptr(st['lap_counts']),
+                                                  nat.ptr(st['scans_u24']))
             io['_actions_dev'] = torch.zeros((NA, 2), dtype=torch.float64, device=dev)
             io['_ev_tick'] = torch.cuda.Event()
             io['_ev_copy'] = torch.cuda.Event()

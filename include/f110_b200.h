@@ -182,6 +182,10 @@ typedef struct {
     double *collisions;     /* [N*A] */
     uint8_t *done;          /* [N] */
     double *lap_times, *lap_counts;   /* [N*A] */
+    uint8_t *scans_u24;     /* [N*A][B][3] optional narrow scan block for PCIe-bound host consumers (f110_step_host_async only,
+                               used when `scans` is NULL): each range as 24-bit fixed point, little endian, value = q * 2^-19 m
+                               (step 1.9e-6 m = the fp32 scan's own resolution at 30 m; |error| <= 9.6e-7 m; a noisy range
+                               below 0 clamps to 0).  3 bytes per beam instead of 4: see f110_pack_scans_u24. */
 } f110_host_obs;
 int f110_step_host(const f110_sim *sim, const f110_map *map, const f110_beams *beams,
                    const double *actions_host, double *actions_dev_scratch, const f110_host_obs *out,
@@ -198,6 +202,11 @@ int f110_step_host_async(const f110_sim *sim, const f110_map *map, const f110_be
                          const double *actions_host, double *actions_dev_scratch, const f110_host_obs *stage,
                          const f110_host_obs *out, void *compute_stream, void *copy_stream, void *ev_tick_done,
                          void *ev_copy_done);
+
+/* scans [count] fp32 (device) -> out [count][3] bytes (device): q = round(range * 2^19) clamped to [0, 2^24-1], little endian.
+ * No reference counterpart (the reference hands numpy arrays to a policy in the same process); batch extension for host-side
+ * consumers behind PCIe.  Decode: (b0 | b1 << 8 | b2 << 16) * 2^-19. */
+int f110_pack_scans_u24(const float *scans, int64_t count, uint8_t *out, void *stream);
 
 /* ---- standalone kernels (unit-parity surface; device pointers) ------------------------------- */
 

@@ -276,6 +276,38 @@ def test_levine_env_pgm(f110, dev):
     assert isinstance(obs['poses_x'][0], float) and obs['lap_counts'].shape == (1,)
 
 
+def test_packed_u24_host_observation(f110, dev, example_map):
+    """Opt-in narrow host observation (f110_pack_scans_u24 inside f110_step_host_async): the decoded ranges equal
+    round(fp32 range * 2^19) * 2^-19, i.e. within 9.6e-7 m of the fp32 scan; everything else is the fp32 pipeline's."""
+    N, A, T = 32, 2, 6
+    rng = np.random.default_rng(11)
+    poses = _start_poses(f110, rng, N, A, 5)
+    sims = []
+    for packed in (False, True):
+        sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev)
+        sim.set_device_map(example_map)
+        sim.env_reset(poses)
+        sims.append((sim, sim.make_host_pipeline(depth=2, packed_scans=packed)))
+    acts = np.stack([rng.uniform(-0.4189, 0.4189, (T, N * A)), rng.uniform(0, 8, (T, N * A))], axis=2)
+    for t in range(T):
+        for sim, sets in sims:
+            io = sets[t % 2]
+            sim.wait_host(io)
+            io['actions'].numpy()[:] = acts[t]
+            sim.step_host_async(io)
+    for sim, sets in sims:
+        for io in sets:
+            sim.wait_host(io)
+    last = (T - 1) % 2
+    f32 = sims[0][1][last]['scans'].numpy()
+    dec = f110.Simulator.unpack_scans_u24(sims[1][1][last]['scans_u24'])
+    assert dec.shape == f32.shape and dec.dtype == np.float32
+    expect = (np.rint(np.clip(f32, 0, None).astype(np.float64) * 2.0 ** 19) * 2.0 ** -19).astype(np.float32)
+    assert np.array_equal(dec, expect)
+    assert np.abs(dec.astype(np.float64) - f32).max() <= 2.0 ** -20 + 1e-12
+    assert np.array_equal(sims[0][1][last]['state'].numpy(), sims[1][1][last]['state'].numpy())
+
+
 # ----------------------------------------------------------------------------- auto-reset keeps the episode end visible
 def test_tick_autoreset_latches_done(f110, dev, example_map):
     """with the fused tick + auto-reset a collision-terminated episode must still show done = 1 (the

@@ -879,6 +879,30 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.attrs = at; cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+// launch in thread-block clusters of `cl` CTAs (grid must be a multiple of cl)
+template <typename... KArgs, typename... Args>
+static void launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, unsigned cl, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+// does a grid of `blocks` CTAs in clusters of CL fit on the device at once?  (a persistent kernel needs all of them resident)
+template <typename K>
+static bool clusters_fit(K kernel, unsigned blocks, unsigned threads, unsigned cl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    return (unsigned)n * cl >= blocks;
+}
 
 template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false, int PT = 512>
 static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
@@ -889,9 +913,36 @@ static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks,
 }
 static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool cells, bool coded, bool occ3, bool layered,
                         bool noise, bool count, bool dyn, cudaStream_t st) {
-    // A/B of the block shape at the same 64 warps/SM: 2 x 1024 threads (variant 60), 8 x 256 (variant 61)
-    if (cells && !layered && !coded && rm_variant() == 60) { launch_lean_t<0, true, false, 2, false, 1024>(q, mq, sms * 2u, noise, count, st); return; }
-    if (cells && !layered && !coded && rm_variant() == 61) { launch_lean_t<0, true, false, 8, false, 256>(q, mq, sms * 8u, noise, count, st); return; }
+    // thread-block clusters sharing one ticket counter (variants 62-65), plain noise-free marching only
+    if (cells && !layered && !coded && !noise && !count && rm_variant() >= 62 && rm_variant() <= 65) {
+        const int v = rm_variant();
+        bool ok = false;
+        if (v == 62) { auto k = k_march_lean<0, false, false, true, false, 1024, 2, false, 4>;
+                       if ((ok = clusters_fit(k, sms * 2u / 4u * 4u, 1024, 4))) launch_cluster(k, dim3(sms * 2u / 4u * 4u), dim3(1024), 4, st, q, mq); }
+        if (v == 63) { auto k = k_march_lean<0, false, false, true, false, 1024, 2, false, 2>;
+                       if ((ok = clusters_fit(k, sms * 2u, 1024, 2))) launch_cluster(k, dim3(sms * 2u), dim3(1024), 2, st, q, mq); }
+        if (v == 64) { auto k = k_march_lean<0, false, false, true, false, 512, 4, false, 4>;
+                       if ((ok = clusters_fit(k, sms * 4u, 512, 4))) launch_cluster(k, dim3(sms * 4u), dim3(512), 4, st, q, mq); }
+        if (v == 65) { auto k = k_march_lean<0, false, false, true, false, 512, 4, false, 8>;
+                       if ((ok = clusters_fit(k, sms * 4u / 8u * 8u, 512, 8))) launch_cluster(k, dim3(sms * 4u / 8u * 8u), dim3(512), 8, st, q, mq); }
+        if (ok) return;
+        if (getenv("F110_DEBUG")) fprintf(stderr, "f110: cluster variant %d does not fit, using the default launch\n", v);
+    }
+    // Block shape at the same 64 warps/SM.  Two 1024-thread blocks per SM (32 warps share a ticket counter, the queue is dealt
+    // to half as many blocks) beat four 512-thread blocks whenever a block gets enough items -- cfg3 march 443 -> 420 us,
+    // cfg5_2160 819 -> 761, cfg2x2 120.2 -> 116.2 -- and lose when it does not: cfg2 (470 items per big block) 68.2 -> 70.5 us
+    // (profiles/r2/ab_march_7_*.jsonl, ab_march_8_*.jsonl).  Variant 60 / 61 / 66 force 2 x 1024 / 8 x 256 / 4 x 512.
+    const int v = rm_variant();
+    const bool big = (v == 60) || (v != 61 && v != 66 && v != 21 && v != 22 && !dyn && !coded && !occ3 &&
+                                   (unsigned long long)mq.items >= 700ull * 2ull * (unsigned long long)sms);
+    if (big && !coded) {
+        if (!cells && layered) launch_lean_t<0, false, true, 2, false, 1024>(q, mq, sms * 2u, noise, count, st);
+        else if (!cells) launch_lean_t<0, false, false, 2, false, 1024>(q, mq, sms * 2u, noise, count, st);
+        else if (layered) launch_lean_t<0, true, true, 2, false, 1024>(q, mq, sms * 2u, noise, count, st);
+        else launch_lean_t<0, true, false, 2, false, 1024>(q, mq, sms * 2u, noise, count, st);
+        return;
+    }
+    if (cells && !layered && !coded && v == 61) { launch_lean_t<0, true, false, 8, false, 256>(q, mq, sms * 8u, noise, count, st); return; }
     if (dyn && cells && !layered && !coded) {
         if (occ3) launch_lean_t<0, true, false, 3, true>(q, mq, sms * 3u, noise, count, st);
         else launch_lean_t<0, true, false, 4, true>(q, mq, sms * 4u, noise, count, st);

@@ -113,7 +113,12 @@ __device__ __noinline__ double redo_beam_cells(const double *__restrict__ table,
 // (Handing out the WHOLE queue dynamically loses: 17 k same-address atomics per tick queue up behind each other and
 // the claim is late more often than not -- 80.6 us vs 69.0 us at cfg2, profiles/r2/ab_march.md.)
 #define F110_DYN_RING 16u
-template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB, bool DYN = false>
+// CL > 1: the kernel is launched in thread-block clusters of CL CTAs that share ONE ticket counter (the shared-memory word of
+// the cluster's rank-0 CTA, popped through distributed shared memory: mapa + atom.shared::cluster).  The queue is then dealt
+// statically to the CLUSTERS and handed out dynamically inside each: a pool of CL x PT/32 warps on several SMs of one GPC
+// instead of PT/32 warps on one SM, which evens out the finishing times without the global atomics that made the fully
+// dynamic queue lose (profiles/r2/README.md).
+template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB, bool DYN = false, int CL = 1>
 __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
     __shared__ unsigned s_run[DYN ? F110_DYN_RING : 1u], s_seq[DYN ? F110_DYN_RING : 1u];
@@ -132,15 +137,25 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
     const unsigned nAB = nA + nB;
     const unsigned total = min(nAB + min(mq.count[2], mq.items), mq.items);
     const unsigned cs = mq.chunk_shift;
-    const unsigned qstride = gridDim.x << cs, qbase = blockIdx.x << cs, qmask = (1u << cs) - 1u;
-    const unsigned s_next_addr = (unsigned)__cvta_generic_to_shared(&s_next);
+    const unsigned qstride = (gridDim.x / (unsigned)CL) << cs, qbase = (blockIdx.x / (unsigned)CL) << cs, qmask = (1u << cs) - 1u;
+    unsigned s_next_addr = (unsigned)__cvta_generic_to_shared(&s_next);
+    if (CL > 1) {
+        // every CTA pops the counter of the cluster's rank-0 CTA; it was zeroed before the __syncthreads above, the cluster
+        // barrier makes that visible to the other CTAs before their first pop
+        asm volatile("mapa.shared::cluster.u32 %0, %0, 0;" : "+r"(s_next_addr));
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     unsigned looks = 0u;
     for (;;) {
         // one elected lane pops the block's queue.  (An atomicAdd inside `if (lane == 0)` makes ptxas emit its
         // warp-aggregation sequence -- vote, find-leader, two popc, shuffle: 14 extra instructions per item.)
         unsigned k = 0, leader;
-        asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
-                     : "+r"(k), "=r"(leader) : "r"(s_next_addr) : "memory");
+        if (CL > 1)
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared::cluster.add.u32 %0, [%2], 1;\n\t}"
+                         : "+r"(k), "=r"(leader) : "r"(s_next_addr) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
+                         : "+r"(k), "=r"(leader) : "r"(s_next_addr) : "memory");
         k = __shfl_sync(0xffffffffu, k, leader);
         unsigned q;
         if (DYN) {
@@ -261,6 +276,8 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
         const unsigned nsum = __reduce_add_sync(0xffffffffu, looks);
         if (lane == 0 && nsum) atomicAdd(p.lookup_counter, (unsigned long long)nsum);
     }
+    // the rank-0 CTA's shared memory must outlive the last pop of every CTA of the cluster
+    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace f110

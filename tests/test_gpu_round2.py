@@ -202,6 +202,28 @@ def test_metre_march_variants_vs_oracle(f110, dev, variant, name, v):
     assert sim.lookups() == sum(o.nlook for o in osims)
 
 
+@pytest.mark.parametrize('v', [60, 61, 62, 63, 64, 65, 66])
+def test_block_shape_and_cluster_variants_bit_identical(f110, dev, example_map, variant, v):
+    """Block shapes (2 x 1024, 8 x 256 threads per SM) and the thread-block-cluster launches that share one ticket counter
+    through distributed shared memory: same scans, state and collisions as the default launch, bit for bit."""
+    N, A, T = 96, 2, 12
+    rng = np.random.default_rng(4242)
+    poses = _start_poses(f110, rng, N, A, 5)
+    acts = np.stack([rng.uniform(-0.4189, 0.4189, (T, N, A)), rng.uniform(0, 8, (T, N, A))], axis=3)
+    out = []
+    for vv in (0, v):
+        variant(vv)
+        sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev)
+        sim.set_device_map(example_map)
+        sim.env_reset(poses)
+        for t in range(T):
+            sim.tick(acts[t], env_level=True)
+        torch.cuda.synchronize()
+        out.append((cpu(sim.scans).copy(), cpu(sim.state).copy(), cpu(sim.collisions).copy()))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 def test_march_item_beams_64(f110, dev, example_map, variant):
     """64-beam work items (Simulator(march_item_beams=64)) run on the round-1 persistent kernel <SUB=2>."""
     for B in (1080, 270):

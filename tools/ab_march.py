@@ -6,7 +6,9 @@
 For every (workload, variant): reset to the same start poses, replay the same action sequence, time each kernel of
 the tick with CUDA events (f110_step_profile, L2 flushed between ticks) and the whole tick as a CUDA-graph replay,
 and hash the scans / state so that the variants are shown to produce identical results.
-Variants (F110_MARCH_VARIANT): 0 lean fp64 table, 64 warps/SM; 21 same at 48 warps/SM (40 registers);
+Variants (F110_MARCH_VARIANT): 0 lean fp64 table, 64 warps/SM, block shape chosen by the item count (2 x 1024 threads per SM
+when a block gets >= 700 items, else 4 x 512); 60 / 66 / 61 force 2 x 1024 / 4 x 512 / 8 x 256; 62-65 thread-block clusters sharing
+one ticket counter through DSMEM; 40 / 41 dynamic queue tail; 30 / 31 TMA tile; 21 lean at 48 warps/SM (40 registers);
 20 / 22 lean, u8 rank-coded table + shared-memory LUT (64 / 48 warps); 1 round-1 persistent kernel; 6 round-1 coded;
 7 no queue (block per 64-beam tile); 30+ see csrc/f110_b200.cu.
 """

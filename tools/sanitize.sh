@@ -23,11 +23,11 @@ for variant in (0, 30):
     sim.set_device_map(dmap)
     rng = np.random.default_rng(0)
     k = rng.integers(0, wp_np.shape[0], N)
-    sim.env_reset(np.stack([np.stack([wp_np[kk], wp_np[(kk - 4) % len(wp_np)]]) for kk in k]))
+    sim.env_reset(np.stack([np.stack([wp_np[kk], wp_np[(kk - 2) % len(wp_np)]]) for kk in k]))   # 0.4 m apart: bodies overlap -> GJK contact -> auto-reset
     resets = 0
     for t in range(30):
         act = np.stack([rng.uniform(-0.4189, 0.4189, (N, A)), rng.uniform(4, 8, (N, A))], axis=2)
-        sim.tick(act, env_level=True, autoreset_poses=wp, pose_gap=4)
+        sim.tick(act, env_level=True, autoreset_poses=wp, pose_gap=(2 if t < 15 else 23))
         resets += int(sim.done.sum().item())
     torch.cuda.synchronize()
     print('variant', variant, 'ticks 30 episodes ended', resets, 'scan checksum %.3f' % float(sim.scans.double().sum()))

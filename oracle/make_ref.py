@@ -36,6 +36,12 @@ def make(verbose=True):
             manifest[f] = hashlib.sha256(fh.read()).hexdigest()
     with open(os.path.join(DST, 'MANIFEST.json'), 'w') as fh:
         json.dump({'source': src_dir, 'sha256': manifest}, fh, indent=1)
+    with open(os.path.join(DST, 'README.txt'), 'w') as fh:
+        fh.write('oracle/_ref/ holds UNMODIFIED modules of the reference (f1tenth/f1tenth_gym), copied byte for byte by\n'
+                 'oracle/make_ref.py when __graft_entry__.build() runs in the build container (VERDICT r1, next-round item 6).\n'
+                 'The directory is git-ignored: nothing in it is part of this repository or of the product.  It exists so that\n'
+                 'bench.py --impl reference / cpu_baseline can time the reference\'s own numba path on the GPU box, which has no\n'
+                 '/root/reference.  sha256 of every file: MANIFEST.json.\n')
     if verbose:
         print('make_ref: %d reference modules -> %s' % (len(FILES), dst_dir))
     return True

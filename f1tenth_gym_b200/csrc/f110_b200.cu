@@ -819,7 +819,10 @@ static int num_sms() {
 // A/B switch for measurements (profiles/): F110_MARCH_VARIANT = 0 default (persistent queue, fp64 cell table),
 // 6 = rank-coded byte table, 7 = no queue (one block per 64-beam tile), 9 = no queue, 40 registers
 static int g_variant = -1, g_chunk = -1;
-static int g_dyn_pct = 85, g_dyn_ahead = 4;      // dynamic queue tail of k_march_lean<DYN> (variants 40 / 41)
+// Dynamic second half of the queue (k_march_lean<DYN>): every block gets g_dyn_pct % of its fair share dealt statically and claims
+// the rest in runs from one global counter, g_dyn_ahead runs ahead of their use.  50 % / 4 is the measured optimum (cfg3 march
+// 419 -> 407 us, cfg2x2 116 -> 113.6, cfg2 68.5 -> 68.1; profiles/r2/ab_march_11..13_*.jsonl): the default of variant 0.
+static int g_dyn_pct = 50, g_dyn_ahead = 4;
 static int rm_variant() {
     if (g_variant < 0) {
         const char *e = getenv("F110_MARCH_VARIANT");
@@ -943,6 +946,7 @@ static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool
         return;
     }
     if (cells && !layered && !coded && v == 61) { launch_lean_t<0, true, false, 8, false, 256>(q, mq, sms * 8u, noise, count, st); return; }
+    if (dyn && cells && !layered && !coded && v == 42) { launch_lean_t<0, true, false, 2, true, 1024>(q, mq, sms * 2u, noise, count, st); return; }
     if (dyn && cells && !layered && !coded) {
         if (occ3) launch_lean_t<0, true, false, 3, true>(q, mq, sms * 3u, noise, count, st);
         else launch_lean_t<0, true, false, 4, true>(q, mq, sms * 4u, noise, count, st);
@@ -1167,7 +1171,9 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
             mq.claim = sim->march_count + 3;
             {   // dynamic tail of the queue (k_march_lean<DYN>): g_dyn_pct % of every block's share is dealt statically
                 const unsigned runs = (mq.items + (1u << mq.chunk_shift) - 1u) >> mq.chunk_shift;
-                const unsigned blocks = (unsigned)num_sms() * 4u;
+                // (blocks of the lean launch: 2 per SM when the big shape is chosen -- same rule as launch_lean)
+                const bool big_blocks = (variant == 42);      // the dynamic default (variants 0 / 40 / 41) runs 4 x 512 threads per SM
+                const unsigned blocks = (unsigned)num_sms() * (big_blocks ? 2u : 4u);
                 mq.dyn_ahead = (unsigned)g_dyn_ahead;
                 mq.static_runs = (unsigned)((unsigned long long)runs * (unsigned)g_dyn_pct / 100ull / blocks);
             }
@@ -1212,7 +1218,8 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                 if ((rc = launch_tile(t, map, tile_sz, (unsigned)num_sms(), noise, count, st))) return rc;
             } else
             launch_lean(q, mq, (unsigned)num_sms(), cell_units, lcoded, occ3, layered, noise, count,
-                        /* dynamic queue tail: */ (variant == 40 || variant == 41) && mq.static_runs >= mq.dyn_ahead, st);
+                        /* dynamic queue tail: */ (variant == 0 || variant == 40 || variant == 41 || variant == 42) && !layered &&
+                            mq.static_runs >= mq.dyn_ahead, st);
         } else if (queued) {
             const unsigned blocks = (unsigned)num_sms() * 4u;
             if (!cell_units) launch_persistent<512, 1, false>(k, mq, blocks, coded, noise, count, st);

@@ -113,6 +113,28 @@ __device__ __noinline__ double redo_beam_cells(const double *__restrict__ table,
 // (Handing out the WHOLE queue dynamically loses: 17 k same-address atomics per tick queue up behind each other and
 // the claim is late more often than not -- 80.6 us vs 69.0 us at cfg2, profiles/r2/ab_march.md.)
 #define F110_DYN_RING 16u
+__device__ __noinline__ unsigned dyn_queue_position(unsigned k, bool elected, unsigned cs, unsigned static_runs, unsigned dyn_ahead,
+                                                    unsigned *claim, unsigned *s_run, unsigned *s_seq, unsigned qstride,
+                                                    unsigned qbase, unsigned nblocks) {
+    const unsigned r = k >> cs, idx = k & ((1u << cs) - 1u);
+    if (idx == 0u && elected && r + dyn_ahead >= static_runs) {
+        // first ticket of run r: claim the dynamic run that local run r + dyn_ahead will use
+        const unsigned g = atomicAdd(claim, 1u);
+        const unsigned nb = (r + dyn_ahead) & (F110_DYN_RING - 1u);
+        ((volatile unsigned *)s_run)[nb] = static_runs * nblocks + g;
+        __threadfence_block();
+        ((volatile unsigned *)s_seq)[nb] = r + dyn_ahead;
+    }
+    if (r < static_runs) return r * qstride + qbase + idx;
+    const unsigned buf = r & (F110_DYN_RING - 1u);
+    unsigned sq;
+    while ((sq = ((volatile unsigned *)s_seq)[buf]) != r) {
+        // a ring slot is reused 16 runs (>= 64 tickets) later: a warp cannot fall that far behind between drawing its ticket
+        // and reading the slot; if it ever did, stop loudly instead of marching the wrong items
+        if (sq != 0xFFFFFFFFu && sq > r) __trap();
+    }
+    return (((volatile unsigned *)s_run)[buf] << cs) + idx;
+}
 // CL > 1: the kernel is launched in thread-block clusters of CL CTAs that share ONE ticket counter (the shared-memory word of
 // the cluster's rank-0 CTA, popped through distributed shared memory: mapa + atom.shared::cluster).  The queue is then dealt
 // statically to the CLUSTERS and handed out dynamically inside each: a pool of CL x PT/32 warps on several SMs of one GPC
@@ -159,28 +181,10 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
         k = __shfl_sync(0xffffffffu, k, leader);
         unsigned q;
         if (DYN) {
-            const unsigned r = k >> cs;
-            if ((k & qmask) == 0u && lane == leader && r + mq.dyn_ahead >= mq.static_runs) {
-                // first ticket of run r: claim the dynamic run that local run r + dyn_ahead will use
-                const unsigned g = atomicAdd(mq.claim, 1u);
-                const unsigned nb = (r + mq.dyn_ahead) & (F110_DYN_RING - 1u);
-                s_run[nb] = mq.static_runs * gridDim.x + g;
-                __threadfence_block();
-                *(volatile unsigned *)&s_seq[nb] = r + mq.dyn_ahead;
-            }
-            if (r < mq.static_runs) {
-                q = r * qstride + qbase + (k & qmask);
-            } else {
-                const unsigned buf = r & (F110_DYN_RING - 1u);
-                unsigned sq;
-                while ((sq = *(volatile unsigned *)&s_seq[buf]) != r) {
-                    // a ring slot is reused 16 runs (>= 64 tickets) later: a warp cannot fall that far behind between
-                    // drawing its ticket and reading the slot; if it ever did, stop loudly instead of marching wrong items
-                    if (sq != 0xFFFFFFFFu && sq > r) __trap();
-                }
-                __threadfence_block();
-                q = (s_run[buf] << cs) + (k & qmask);
-            }
+            // out of line: inlined, the ring logic costs the whole item path its register allocation (ncu: 55.4 M instead of
+            // 43.6 M warp-instructions per launch at cfg2 -- the clamp and the store of every beam grew)
+            q = dyn_queue_position(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride, qbase,
+                                   gridDim.x);
         } else {
             q = (k >> cs) * qstride + qbase + (k & qmask);
         }

@@ -224,6 +224,36 @@ def test_block_shape_and_cluster_variants_bit_identical(f110, dev, example_map, 
         assert np.array_equal(a, b)
 
 
+def test_dynamic_queue_large_batch(f110, dev, example_map, variant):
+    """The default hands out half of the queue dynamically -- but only when every block has enough runs, which the small
+    batches of the other tests never reach.  2048 envs (69632 items = 14 runs per block: 7 static, 7 dynamic): identical to
+    the static launch (variant 66) bit for bit, and a sample of envs is checked against the oracle."""
+    import oracle
+    N, A, T = 2048, 1, 6
+    rng = np.random.default_rng(99)
+    poses = _start_poses(f110, rng, N, A)
+    acts = np.stack([rng.uniform(-0.4189, 0.4189, (T, N, A)), rng.uniform(0, 8, (T, N, A))], axis=3)
+    out = {}
+    for vv in (66, 0, 42):
+        variant(vv)
+        sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev, count_lookups=(vv != 42))
+        sim.set_device_map(example_map)
+        sim.reset(poses)
+        for t in range(T):
+            sim.tick(acts[t], env_level=False)
+        torch.cuda.synchronize()
+        out[vv] = (cpu(sim.scans).copy(), cpu(sim.state).copy(), sim.lookups())
+    assert np.array_equal(out[0][0], out[66][0]) and np.array_equal(out[0][1], out[66][1]) and out[0][2] == out[66][2]
+    assert np.array_equal(out[42][0], out[66][0])
+    omap = _omap(example_map)
+    for e in range(0, N, 97):
+        o = oracle.OracleSim(omap, num_agents=A)
+        o.reset(poses[e])
+        for t in range(T):
+            o.step(acts[t, e])
+        assert np.array_equal(out[0][0][e], o.scans[0].astype(np.float32)), e
+
+
 def test_march_item_beams_64(f110, dev, example_map, variant):
     """64-beam work items (Simulator(march_item_beams=64)) run on the round-1 persistent kernel <SUB=2>."""
     for B in (1080, 270):

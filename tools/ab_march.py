@@ -6,8 +6,9 @@
 For every (workload, variant): reset to the same start poses, replay the same action sequence, time each kernel of
 the tick with CUDA events (f110_step_profile, L2 flushed between ticks) and the whole tick as a CUDA-graph replay,
 and hash the scans / state so that the variants are shown to produce identical results.
-Variants (F110_MARCH_VARIANT): 0 lean fp64 table, 64 warps/SM, block shape chosen by the item count (2 x 1024 threads per SM
-when a block gets >= 700 items, else 4 x 512); 60 / 66 / 61 force 2 x 1024 / 4 x 512 / 8 x 256; 62-65 thread-block clusters sharing
+Variants (F110_MARCH_VARIANT): 0 lean fp64 table, 64 warps/SM, 4 x 512 threads per SM, first half of every block's share dealt
+statically and the rest claimed dynamically (--dyn static_pct:ahead); 66 / 60 / 61 static dealing with 4 x 512 / 2 x 1024 / 8 x 256
+threads per SM; 42 dynamic with 2 x 1024; 62-65 thread-block clusters sharing
 one ticket counter through DSMEM; 40 / 41 dynamic queue tail; 30 / 31 TMA tile; 21 lean at 48 warps/SM (40 registers);
 20 / 22 lean, u8 rank-coded table + shared-memory LUT (64 / 48 warps); 1 round-1 persistent kernel; 6 round-1 coded;
 7 no queue (block per 64-beam tile); 30+ see csrc/f110_b200.cu.
@@ -29,7 +30,7 @@ import f1tenth_gym_b200 as f110   # noqa: E402
 from f1tenth_gym_b200 import _native as nat   # noqa: E402
 
 
-def run(workload, variant, ticks, dev, chunk=3, dyn=(85, 4), pdl=0, tail=8):
+def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8):
     w = bench.WORKLOADS[workload]
     N, A, B = w['num_envs'], w['num_agents'], w['num_beams']
     NA = N * A
@@ -91,7 +92,7 @@ def main():
     ap.add_argument('--workloads', default='cfg2,cfg2x2,cfg3')
     ap.add_argument('--variants', default='1,0,21,20,22')
     ap.add_argument('--chunks', default='3')
-    ap.add_argument('--dyn', default='85:4', help='static_pct:ahead[,static_pct:ahead...] for the dynamic-tail variants 40/41')
+    ap.add_argument('--dyn', default='50:4', help='static_pct:ahead[,static_pct:ahead...] for the dynamic-tail variants 40/41')
     ap.add_argument('--pdl', default='0')
     ap.add_argument('--tail', default='8', help='k_tail register budget: 4 (128 regs), 5 (96), 8 (64)')
     ap.add_argument('--ticks', type=int, default=40)
@@ -103,7 +104,7 @@ def main():
         for rep in range(args.repeat):
             for v in [int(x) for x in args.variants.split(',')]:
                 for ch in [int(x) for x in args.chunks.split(',')]:
-                    for dy in (args.dyn.split(',') if v in (40, 41) else ['85:4']):
+                    for dy in (args.dyn.split(',') if v in (0, 40, 41, 42) else ['50:4']):
                         for pdl in [int(x) for x in args.pdl.split(',')]:
                             for tl in [int(x) for x in args.tail.split(',')]:
                                 r = run(wl, v, args.ticks, dev, ch, tuple(int(x) for x in dy.split(':')), pdl, tl)

@@ -107,11 +107,14 @@ __device__ __noinline__ double redo_beam_cells(const double *__restrict__ table,
 // DYN: the first mq.static_runs runs (of 2^chunk_shift consecutive queue entries) of every block are dealt statically,
 // round-robin, as before; the REST of the queue is handed out dynamically from one global counter (mq.claim).  Static
 // dealing gives every block the same number of items but not the same amount of work: ncu showed the SMs busy for only
-// 83 % of the kernel's duration (profiles/r2: sm__cycles_active.avg 106.8 k of 127.8 k elapsed cycles).  Claims are
-// prefetched: the warp that draws the first ticket of local run r claims the run for r + mq.dyn_ahead and publishes it in
-// a shared-memory ring, so a ticket only reads two shared words; the global order of the queue (longest first) is kept.
-// (Handing out the WHOLE queue dynamically loses: 17 k same-address atomics per tick queue up behind each other and
-// the claim is late more often than not -- 80.6 us vs 69.0 us at cfg2, profiles/r2/ab_march.md.)
+// 83 % of the kernel's duration at cfg2 and 95 % at cfg3 (profiles/r2).  Claims are prefetched: the warp that draws the first
+// ticket of local run r claims the run for r + mq.dyn_ahead and publishes it in a shared-memory ring, so a ticket only reads
+// two shared words; the global order of the queue (longest first) is kept.  Two lessons from the A/B (profiles/r2/README.md):
+//   * the ring logic must stay OUT OF LINE (dyn_queue_position): inlined it wrecks the register allocation of the whole item
+//     path (55.4 M instead of 43.6 M warp-instructions per launch) and every dynamic flavour loses by 15-25 %;
+//   * half static / half dynamic is the optimum (cfg3 march 443 -> 407 us with 4 x 512 threads per SM, better than the static
+//     2 x 1024 shape's 419; 85 % static loses, 10-30 % is 1-2 % behind): the static half keeps the head of the queue -- the
+//     heavy items -- free of claim latency, the dynamic half evens out the blocks.
 #define F110_DYN_RING 16u
 __device__ __noinline__ unsigned dyn_queue_position(unsigned k, bool elected, unsigned cs, unsigned static_runs, unsigned dyn_ahead,
                                                     unsigned *claim, unsigned *s_run, unsigned *s_seq, unsigned qstride,

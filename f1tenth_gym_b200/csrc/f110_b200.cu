@@ -1,11 +1,14 @@
 // f110_b200.cu — kernels and C ABI of libf110_b200.so (see include/f110_b200.h).
 //
 // One tick (reference base_classes.py:553-612 Simulator.step) = three launches on the caller's stream:
-//   k_dynamics   thread per agent   steer FIFO, pid, RK4/Euler, yaw wrap, scan pose, pose snapshot
-//   k_raymarch   thread per beam    LUT heading, sphere tracing on the DT grid, fused iTTC predicate,
-//                                   optional seeded noise, fp32 range out (the roofline kernel)
-//   k_finalize   warp per agent     GJK vs. the other agents of the env, wall-hit state zeroing,
-//                                   opponent ray-cast inside the blocked-view window, collisions obs
+//   k_dynamics     thread per agent     steer FIFO, pid, RK4/Euler, yaw wrap, scan pose, pose snapshot, the per-agent record of
+//                                       the march (+ extra blocks that sort last tick's work items into the march queue)
+//   k_march_lean   persistent, warp per 32-beam item (march_lean.cuh): LUT heading, sphere tracing on the DT grid, fused iTTC
+//                                       predicate, optional seeded noise, fp32 range out -- the roofline kernel.  Maps with a
+//                                       rotated origin and stand-alone scans run the literal k_raymarch (thread per beam)
+//   k_tail         warp per agent       GJK vs. the other agents of the env, wall-hit state zeroing, opponent ray-cast inside the
+//                                       blocked-view window, collisions obs, then lap logic and auto-reset per env
+//                                       (k_finalize = the same without the env-level part, for f110_step)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (no FMA contraction).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -816,8 +819,11 @@ static int num_sms() {
     return n;
 }
 
-// A/B switch for measurements (profiles/): F110_MARCH_VARIANT = 0 default (persistent queue, fp64 cell table),
-// 6 = rank-coded byte table, 7 = no queue (one block per 64-beam tile), 9 = no queue, 40 registers
+// A/B switch for measurements (profiles/r2/README.md; f110_debug_set_variant or F110_MARCH_VARIANT): 0 = default (k_march_lean,
+// fp64 table, half of the queue dynamic); 66 / 60 / 61 = static dealing with 4 x 512 / 2 x 1024 / 8 x 256 threads per SM;
+// 40 / 41 / 42 = dynamic with 4 x 512 / 3 x 512 / 2 x 1024; 20 / 22 = rank-coded table + shared LUT; 21 = 48 warps/SM;
+// 30 / 31 = TMA tile 128 / 160 cells; 62-65 = thread-block clusters sharing a ticket counter; 1 / 6 = round-1 persistent kernel
+// (fp64 / coded); 7 / 9 = no queue (block per 64-beam tile); 13 = the literal k_raymarch
 static int g_variant = -1, g_chunk = -1;
 // Dynamic second half of the queue (k_march_lean<DYN>): every block gets g_dyn_pct % of its fair share dealt statically and claims
 // the rest in runs from one global counter, g_dyn_ahead runs ahead of their use.  50 % / 4 is the measured optimum (cfg3 march

@@ -651,6 +651,160 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tail(f110_sim s, BeamView bv, in
     if (blockIdx.x == 0 && threadIdx.x == 0) end_of_tick_housekeeping(s);
 }
 
+// ------------------------------------------------------------------------------------ k_tail2 (2 <= A <= 4)
+// Same results as k_tail, reorganised (round 2).  ncu on k_tail at 16384 x 2: 1317 warp-instructions per agent, most of them the
+// per-agent SCALAR prologue (opponent vertices, six atan2, asin, sqrt, nearest-beam searches) that all 32 lanes of the agent's
+// warp execute redundantly (profiles/r2/finalize_cfg3_line_hot.txt).  Here a block owns EPB whole envs and works in three phases:
+//   1. one THREAD per (ego, opponent) pair does the scalar prologue -- 32 pairs per warp instead of one -- and leaves a task
+//      record in shared memory; one thread per agent also does the wall-hit zeroing, GJK and the collisions observation;
+//   2. one WARP per ego walks its tasks and ray-casts the windows beam-parallel (the same loop as finalize_agent);
+//   3. one thread per env: lap logic + auto-reset (as in k_tail).
+struct TailTask {
+    double px, py, yaw, phi, cone;
+    double v[8];
+    int lo, hi, active, pad;
+};
+#define F110_TAIL2_THREADS 256
+
+__global__ void __launch_bounds__(F110_TAIL2_THREADS, 3) k_tail2(f110_sim s, BeamView bv, int env_level, AutoResetArgs ar,
+                                                                  double max_scan_range, int envs_per_block) {
+    extern __shared__ __align__(16) unsigned char tail2_smem[];
+    TailTask *tasks = reinterpret_cast<TailTask *>(tail2_smem);
+    const int A = s.num_agents, NA = s.num_envs * A;
+    const int opp = A - 1;                                    // tasks per agent
+    const int env0 = blockIdx.x * envs_per_block;
+    const int envs_here = min(envs_per_block, s.num_envs - env0);
+    const int agents_here = envs_here * A;
+    const int ntasks = agents_here * opp;
+    pdl_wait();                                                // the march kernel (scans, wall flags) must be complete
+
+    // ---- phase 1: thread per (ego, opponent) pair
+    for (int t = threadIdx.x; t < ntasks; t += blockDim.x) {
+        const int la = t / opp, oj = t - la * opp;
+        const int envl = la / A, slot = la - envl * A;
+        const int env = env0 + envl, a = env * A + slot;
+        const int j = oj < slot ? oj : oj + 1;                 // opponents in ascending index, skipping the ego itself
+        const int hit = s.wall_flag[a];
+        const double *pa = s.agent_poses + 5 * (size_t)a;
+        const double px = pa[0], py = pa[1];
+        // check_ttc zeroes state[3:] -- including the yaw -- before the opponent ray-cast reads it (:246-249, :225)
+        const double yaw = hit ? 0.0 : pa[2];
+        const double cyaw = hit ? 1.0 : pa[3], syaw = hit ? 0.0 : pa[4];
+        const double *pb = s.agent_poses + 5 * (size_t)(env * A + j);
+        if (oj == 0) {
+            // per-agent duties: wall-hit zeroing, GJK against the other agents (collision_multiple :184-212), collisions obs
+            if (hit) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) s.state[(size_t)(3 + q) * NA + a] = 0.0;
+            }
+            int col = 0, cidx = -1;
+            const double reach2 = (s.sim_length * s.sim_length + s.sim_width * s.sim_width) * 1.001;
+            for (int jj = 0; jj < A; jj++) {
+                if (jj == slot) continue;
+                const double *pc = s.agent_poses + 5 * (size_t)(env * A + jj);
+                const double ddx = pc[0] - pa[0], ddy = pc[1] - pa[1];
+                if (ddx * ddx + ddy * ddy > reach2) continue;
+                double vme[8], vo[8];
+                get_vertices_cs(pa[0], pa[1], pa[3], pa[4], s.sim_length, s.sim_width, vme);
+                get_vertices_cs(pc[0], pc[1], pc[3], pc[4], s.sim_length, s.sim_width, vo);
+                const bool c = (slot < jj) ? gjk_collision(vme, vo) : gjk_collision(vo, vme);
+                if (c) { col = 1; cidx = max(cidx, jj); }
+            }
+            s.collisions[a] = (col || hit) ? 1.0 : 0.0;
+            s.collision_idx[a] = cidx;
+        }
+        // ray_cast_agents (:206-227): the scalar part of one opponent
+        TailTask &k = tasks[t];
+        const double *p = s.params + (size_t)(s.params_per_env ? a : slot) * F110_NPARAM;
+        const double length = p[P_LENGTH], width = p[P_WIDTH];
+        const double half_diag = 0.5 * sqrt(length * length + width * width);
+        const double ddx = pb[0] - px, ddy = pb[1] - py;
+        const double far = max_scan_range + half_diag;
+        int active = 1;
+        if (ddx * ddx + ddy * ddy > far * far) active = 0;     // cannot shorten any beam (see finalize_agent)
+        k.active = active;
+        if (active) {
+            double v[8];
+            get_vertices_cs(pb[0], pb[1], pb[3], pb[4], length, width, v);
+            int lo, hi;
+            double phi;
+            blocked_view_indices_cs(px, py, cyaw, syaw, v, bv.scan_angles, bv.num_beams, bv.fov, bv.angle_increment, pb[0], pb[1],
+                                    lo, hi, phi);
+            double cone = 4.0;
+            if (hi - lo >= 96) {
+                const double dist = sqrt(ddx * ddx + ddy * ddy);
+                if (dist > 1.25 * half_diag) cone = asin(half_diag / dist) + 0.05;
+            }
+            k.px = px; k.py = py; k.yaw = yaw; k.phi = phi; k.cone = cone; k.lo = lo; k.hi = hi;
+#pragma unroll
+            for (int q = 0; q < 8; q++) k.v[q] = v[q];
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: warp per ego, its opponents one after the other (they update the same scan)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int la = warp; la < agents_here; la += nwarps) {
+        const int a = env0 * A + la;
+        float *scan = s.scans + (size_t)a * bv.num_beams;
+        for (int oj = 0; oj < opp; oj++) {
+            const TailTask &k = tasks[la * opp + oj];
+            if (!k.active) continue;
+            const double px = k.px, py = k.py, yaw = k.yaw, phi = k.phi, cone = k.cone;
+            const int lo = k.lo, hi = k.hi;
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = k.v[q];
+            auto cast_beams = [&](int i0, int i1) {
+                for (int i = i0 + lane; i <= i1; i += 32) {
+                    const float cur = scan[i];
+                    double bt = yaw + bv.scan_angles[i];
+                    double dl = bt - phi;
+                    dl = dl - (2 * M_PI) * rint(dl * (1.0 / (2 * M_PI)));
+                    const double adl = fabs(dl);
+                    if (adl > cone && (M_PI - adl) > cone) continue;
+                    double v3x, v3y;
+                    sincos(bt + M_PI / 2., &v3y, &v3x);
+                    const double curd = (double)cur;
+                    double r = INFINITY;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        int e2 = (e + 1) & 3;
+                        double d = get_range_below(px, py, v3x, v3y, v[2 * e], v[2 * e + 1], v[2 * e2], v[2 * e2 + 1], curd);
+                        if (d < r) r = d;
+                    }
+                    float rf = (float)r;
+                    if (rf < cur) scan[i] = rf;
+                }
+            };
+            if (cone < 3.5 && hi - lo >= 96) {
+                const double base = phi - yaw, half = bv.fov / 2., inv_inc = 1.0 / bv.angle_increment;
+                const int m0 = max(-3, (int)floor((-half - cone - 0.02 - base) * (1.0 / M_PI))),
+                          m1 = min(5, (int)ceil((half + cone + 0.02 - base) * (1.0 / M_PI)));
+                for (int m = m0; m <= m1; m++) {
+                    const double c = base + (double)m * M_PI;
+                    const double f0 = (c - cone + half) * inv_inc - 2.0, f1 = (c + cone + half) * inv_inc + 2.0;
+                    if (f1 < (double)lo || f0 > (double)hi) continue;
+                    const int i0 = max(lo, (int)floor(fmax(f0, (double)lo))), i1 = min(hi, (int)ceil(fmin(f1, (double)hi)));
+                    cast_beams(i0, i1);
+                }
+            } else {
+                cast_beams(lo, hi);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: env level
+    if ((int)threadIdx.x < envs_here) {
+        const int env = env0 + (int)threadIdx.x;
+        if (env_level) env_post_step_one(s, env);
+        if (ar.start_poses) autoreset_one(s, env, ar);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) end_of_tick_housekeeping(s);
+}
+
 // ------------------------------------------------------------------------------------ standalone kernels
 __global__ void k_rhs(const double *__restrict__ x, const double *__restrict__ u, const double *__restrict__ p,
                       int M, double *__restrict__ f) {
@@ -877,6 +1031,7 @@ static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned bl
 // budget (occupancy beats spills: cfg3 560.0 / 565.1 / 569.3 us for 64 / 96 / 128 registers)
 static int g_pdl = 0;
 static int g_tail_minb = 8;
+static int g_tail2 = 1;          // 2 <= A <= 4: the two-phase k_tail2 (f110_debug_set_tail(-1) switches back to k_tail for the A/B)
 static thread_local bool g_pdl_this_step = false;     // set by step_impl: PDL only when no events are recorded between the kernels
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
@@ -1049,7 +1204,11 @@ void f110_debug_set_dyn(int static_pct, int ahead) {
     g_dyn_ahead = ahead < 1 ? 1 : (ahead > 8 ? 8 : ahead);
 }
 void f110_debug_set_pdl(int on) { g_pdl = on ? 1 : 0; }
-void f110_debug_set_tail(int minb) { g_tail_minb = minb; }
+void f110_debug_set_tail(int minb) {      // -1: k_tail always; -2: k_tail2 whenever 2 <= A <= 4; else k_tail's register budget
+    if (minb == -1) { g_tail2 = 0; g_tail_minb = 8; }
+    else if (minb == -2) { g_tail2 = 2; g_tail_minb = 8; }
+    else { g_tail2 = 1; g_tail_minb = minb; }
+}
 void f110_debug_set_tile_counter(unsigned long long *buf) { g_tile_counter = buf; }
 void f110_debug_set_chunk(int chunk_shift) { g_chunk = (chunk_shift < 0 || chunk_shift > 6) ? 3 : chunk_shift; }
 
@@ -1260,7 +1419,23 @@ marched:
 
     // largest value a scan entry can hold: the max_range clamp plus 8 sigma of the optional noise
     const double max_scan = map->max_range + 8.0 * (sim->noise_std > 0.0 ? sim->noise_std : 0.0) + 1e-3;
-    if (tail && tail->fused && sim->num_agents <= 32) {
+    // k_tail2 pays off once its blocks fill the GPU (one thread runs a pair's six atan2 one after the other: ~5 us of latency
+    // that k_tail spreads over six lanes): cfg3 (32768 agents) tail 79 -> 60 us, tick 518 -> 486 us; cfg2x2 (8192 agents) 28.6 -> 32 us
+    // (profiles/r2/ab_march_16_two_phase_tail.jsonl), hence the size threshold; g_tail2 = 2 forces it (tests)
+    if (sim->num_agents >= 2 && sim->num_agents <= 4 && (g_tail2 == 2 || (g_tail2 == 1 && NA >= 24576))) {
+        // two-phase tail: ~64 agents per block (thread per (ego, opponent) pair for the scalar work, warp per ego for the beams);
+        // f110_step (no lap logic, no auto-reset) runs the same kernel with the env-level phase switched off
+        // up to 64 agents per block, fewer when that would leave SMs without a block (cfg2x2: 4096 envs / 32 = 128 blocks lost
+        // 4 us against 8 envs per block)
+        const int epb = max(1, min(64 / sim->num_agents, sim->num_envs / (4 * num_sms())));
+        const size_t smem = (size_t)epb * sim->num_agents * (sim->num_agents - 1) * sizeof(TailTask);
+        AutoResetArgs no_ar;
+        no_ar.start_poses = nullptr; no_ar.num_start = 0; no_ar.pose_gap = 0; no_ar.seed = 0; no_ar.tick_host = 0;
+        const bool fused = tail && tail->fused;
+        launch_k(k_tail2, dim3((sim->num_envs + epb - 1) / epb), dim3(F110_TAIL2_THREADS), smem, st, g_pdl_this_step && lean, *sim, bv,
+                 fused ? (int)tail->env_level : 0, fused ? tail->ar : no_ar, max_scan, epb);
+        LAUNCH_CHECK("k_tail2");
+    } else if (tail && tail->fused && sim->num_agents <= 32) {
         // whole envs per block, ~4 warps per block: A = 1 -> 4 envs, A = 2 -> 2 envs, A >= 4 -> 1 env
         const int epb = sim->num_agents >= 4 ? 1 : 4 / sim->num_agents;
         const int threads = 32 * sim->num_agents * epb;

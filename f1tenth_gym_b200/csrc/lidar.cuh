@@ -279,6 +279,32 @@ __device__ __forceinline__ void blocked_view_indices_warp(double px, double py, 
     max_ind = __shfl_sync(0xffffffffu, hi, 0);
 }
 
+// laser_models.py:282-315 get_blocked_view_indices, one thread, with the heading given as (cos, sin) like the warp-cooperative
+// version above (bit-identical to it: the same five atan2 arguments, the same min / max); also returns the world direction to
+// the opponent's centre (cx, cy)
+__device__ __forceinline__ void blocked_view_indices_cs(double px, double py, double cos_yaw, double sin_yaw, const double v[8],
+                                                        const double *__restrict__ scan_angles, int num_beams, double fov,
+                                                        double angle_increment, double cx, double cy, int &min_ind, int &max_ind,
+                                                        double &centre_dir) {
+    const double ego_a = atan2(sin_yaw, cos_yaw);
+    centre_dir = atan2(cy - py, cx - px);
+    int lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double vx = v[2 * i] - px, vy = v[2 * i + 1] - py;
+        const double norm = sqrt(vx * vx + vy * vy);
+        const double ax = vx / norm, ay = vy / norm;
+        double angle = ego_a - atan2(ay, ax);
+        if (angle > M_PI) angle = angle - 2 * M_PI;
+        else if (angle < -M_PI) angle = angle + 2 * M_PI;
+        const int ind = nearest_beam(scan_angles, num_beams, fov, angle_increment, -angle);
+        if (i == 0) { lo = hi = ind; }
+        else { lo = min(lo, ind); hi = max(hi, ind); }
+    }
+    min_ind = lo;
+    max_ind = hi;
+}
+
 // laser_models.py:282-315 get_blocked_view_indices
 __device__ __forceinline__ void blocked_view_indices(double px, double py, double yaw, const double v[8],
                                                      const double *__restrict__ scan_angles, int num_beams,

@@ -128,7 +128,7 @@ def test_tick_path_at_wide_poses(f110, dev, variant, name, v):
 
 
 # ----------------------------------------------------------------------------- tick path at other beam counts, variants
-def _rollout_vs_oracle(f110, dev, dmap, N, A, B, T, gap, seed, **simkw):
+def _rollout_vs_oracle(f110, dev, dmap, N, A, B, T, gap, seed, all_tick=False, **simkw):
     import oracle
     rng = np.random.default_rng(seed)
     omap = _omap(dmap)
@@ -142,7 +142,7 @@ def _rollout_vs_oracle(f110, dev, dmap, N, A, B, T, gap, seed, **simkw):
     worst_state, n_col, n_occ = 0.0, 0, 0
     for t in range(T):
         act = np.stack([rng.uniform(-0.4189, 0.4189, (N, A)), rng.uniform(0, 8, (N, A))], axis=2)
-        obs = sim.tick(act, env_level=False) if t % 2 else sim.step(act)
+        obs = sim.tick(act, env_level=False) if (t % 2 or all_tick) else sim.step(act)
         st = cpu(sim.state).reshape(7, N, A).transpose(1, 2, 0)
         sc = cpu(obs['scans'])
         col = cpu(obs['collisions'])
@@ -252,6 +252,43 @@ def test_dynamic_queue_large_batch(f110, dev, example_map, variant):
         for t in range(T):
             o.step(acts[t, e])
         assert np.array_equal(out[0][0][e], o.scans[0].astype(np.float32)), e
+
+
+@pytest.mark.parametrize('A,gap', [(2, 3), (3, 4), (4, 3), (2, 23)])
+def test_two_phase_tail_vs_oracle(f110, dev, example_map, A, gap):
+    """k_tail2 (the fused tick's tail for 2-4 agents per env: thread per (ego, opponent) pair for the scalar work, warp per ego
+    for the beams) on close trains of cars -- GJK contacts, wall hits, front and rear (all-beams) occlusion windows -- against the
+    oracle, every tick through f110_tick; then the same ticks with the one-warp-per-agent k_tail, bit for bit."""
+    L = f110._native.lib()
+    L.f110_debug_set_tail(-2)                      # force k_tail2 (by default it takes over from 24576 agents on)
+    try:
+        n_col, n_occ = _rollout_vs_oracle(f110, dev, example_map, N=20, A=A, B=1080, T=50, gap=gap, seed=3100 + 10 * A + gap,
+                                          all_tick=True)
+    finally:
+        L.f110_debug_set_tail(8)
+    if gap <= 3:                                   # 0.6 m apart: the bodies touch
+        assert n_col > 0
+    rng = np.random.default_rng(77 + A)
+    N, T = 40, 30
+    poses = _start_poses(f110, rng, N, A, gap)
+    acts = np.stack([rng.uniform(-0.4189, 0.4189, (T, N, A)), rng.uniform(0, 8, (T, N, A))], axis=3)
+    wp = torch.from_numpy(f110.maps.load_waypoints()).to(dev)
+    out = []
+    try:
+        for mode in (-2, -1):                      # -2: k_tail2, -1: k_tail
+            L.f110_debug_set_tail(mode)
+            sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev)
+            sim.set_device_map(example_map)
+            sim.env_reset(poses)
+            for t in range(T):
+                sim.tick(acts[t], env_level=True, autoreset_poses=wp, pose_gap=gap)
+            torch.cuda.synchronize()
+            out.append([cpu(x).copy() for x in (sim.scans, sim.state, sim.collisions, sim.collision_idx, sim.done, sim.lap_times,
+                                                sim.toggle_list, sim.current_time)])
+    finally:
+        L.f110_debug_set_tail(8)
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(x, y)
 
 
 def test_march_item_beams_64(f110, dev, example_map, variant):

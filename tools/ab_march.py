@@ -94,7 +94,7 @@ def main():
     ap.add_argument('--chunks', default='3')
     ap.add_argument('--dyn', default='50:4', help='static_pct:ahead[,static_pct:ahead...] for the dynamic-tail variants 40/41')
     ap.add_argument('--pdl', default='0')
-    ap.add_argument('--tail', default='8', help='k_tail register budget: 4 (128 regs), 5 (96), 8 (64)')
+    ap.add_argument('--tail', default='8', help='k_tail register budget: 4 (128 regs), 5 (96), 8 (64); -1 = always k_tail, -2 = always the two-phase k_tail2')
     ap.add_argument('--ticks', type=int, default=40)
     ap.add_argument('--repeat', type=int, default=2)
     args = ap.parse_args()

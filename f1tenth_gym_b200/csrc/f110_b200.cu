@@ -1031,6 +1031,7 @@ static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned bl
 // budget (occupancy beats spills: cfg3 560.0 / 565.1 / 569.3 us for 64 / 96 / 128 registers)
 static int g_pdl = 0;
 static int g_tail_minb = 8;
+static int g_tail2_threads = F110_TAIL2_THREADS, g_tail2_agents = 64;    // block shape of k_tail2 (f110_debug_set_tail2)
 static int g_tail2 = 1;          // 2 <= A <= 4: the two-phase k_tail2 (f110_debug_set_tail(-1) switches back to k_tail for the A/B)
 static thread_local bool g_pdl_this_step = false;     // set by step_impl: PDL only when no events are recorded between the kernels
 template <typename... KArgs, typename... Args>
@@ -1204,9 +1205,13 @@ void f110_debug_set_dyn(int static_pct, int ahead) {
     g_dyn_ahead = ahead < 1 ? 1 : (ahead > 8 ? 8 : ahead);
 }
 void f110_debug_set_pdl(int on) { g_pdl = on ? 1 : 0; }
-void f110_debug_set_tail(int minb) {      // -1: k_tail always; -2: k_tail2 whenever 2 <= A <= 4; else k_tail's register budget
+void f110_debug_set_tail2(int threads, int agents) {
+    g_tail2_threads = (threads >= 32 && threads <= F110_TAIL2_THREADS) ? (threads / 32) * 32 : F110_TAIL2_THREADS;
+    g_tail2_agents = (agents >= 4 && agents <= 64) ? agents : 64;
+}
+void f110_debug_set_tail(int minb) {      // -1: k_tail always; -2 or a register budget: k_tail2 for 2 <= A <= 4 (the default)
     if (minb == -1) { g_tail2 = 0; g_tail_minb = 8; }
-    else if (minb == -2) { g_tail2 = 2; g_tail_minb = 8; }
+    else if (minb == -2) { g_tail2 = 1; g_tail_minb = 8; }
     else { g_tail2 = 1; g_tail_minb = minb; }
 }
 void f110_debug_set_tile_counter(unsigned long long *buf) { g_tile_counter = buf; }
@@ -1419,20 +1424,21 @@ marched:
 
     // largest value a scan entry can hold: the max_range clamp plus 8 sigma of the optional noise
     const double max_scan = map->max_range + 8.0 * (sim->noise_std > 0.0 ? sim->noise_std : 0.0) + 1e-3;
-    // k_tail2 pays off once its blocks fill the GPU (one thread runs a pair's six atan2 one after the other: ~5 us of latency
-    // that k_tail spreads over six lanes): cfg3 (32768 agents) tail 79 -> 60 us, tick 518 -> 486 us; cfg2x2 (8192 agents) 28.6 -> 32 us
-    // (profiles/r2/ab_march_16_two_phase_tail.jsonl), hence the size threshold; g_tail2 = 2 forces it (tests)
-    if (sim->num_agents >= 2 && sim->num_agents <= 4 && (g_tail2 == 2 || (g_tail2 == 1 && NA >= 24576))) {
+    // k_tail2 (2 <= A <= 4): cfg3 tail 79 -> 60 us, tick 518 -> 486 us; cfg2x2 28.5 -> 22.6 us once its blocks are small enough to
+    // fill the GPU (profiles/r2/ab_march_16..18_*.jsonl)
+    if (sim->num_agents >= 2 && sim->num_agents <= 4 && g_tail2) {
         // two-phase tail: ~64 agents per block (thread per (ego, opponent) pair for the scalar work, warp per ego for the beams);
         // f110_step (no lap logic, no auto-reset) runs the same kernel with the env-level phase switched off
         // up to 64 agents per block, fewer when that would leave SMs without a block (cfg2x2: 4096 envs / 32 = 128 blocks lost
         // 4 us against 8 envs per block)
-        const int epb = max(1, min(64 / sim->num_agents, sim->num_envs / (4 * num_sms())));
+        const int epb = max(1, min(g_tail2_agents / sim->num_agents, sim->num_envs / (4 * num_sms())));
         const size_t smem = (size_t)epb * sim->num_agents * (sim->num_agents - 1) * sizeof(TailTask);
         AutoResetArgs no_ar;
         no_ar.start_poses = nullptr; no_ar.num_start = 0; no_ar.pose_gap = 0; no_ar.seed = 0; no_ar.tick_host = 0;
         const bool fused = tail && tail->fused;
-        launch_k(k_tail2, dim3((sim->num_envs + epb - 1) / epb), dim3(F110_TAIL2_THREADS), smem, st, g_pdl_this_step && lean, *sim, bv,
+        // big blocks (>= 48 agents) run 256 threads, small ones 128 (measured: 256:64 best at cfg3, 128:12 at cfg2x2)
+        const int t2 = (g_tail2_threads != F110_TAIL2_THREADS) ? g_tail2_threads : (epb * sim->num_agents >= 48 ? 256 : 128);
+        launch_k(k_tail2, dim3((sim->num_envs + epb - 1) / epb), dim3(t2), smem, st, g_pdl_this_step && lean, *sim, bv,
                  fused ? (int)tail->env_level : 0, fused ? tail->ar : no_ar, max_scan, epb);
         LAUNCH_CHECK("k_tail2");
     } else if (tail && tail->fused && sim->num_agents <= 32) {

@@ -260,7 +260,7 @@ def test_two_phase_tail_vs_oracle(f110, dev, example_map, A, gap):
     for the beams) on close trains of cars -- GJK contacts, wall hits, front and rear (all-beams) occlusion windows -- against the
     oracle, every tick through f110_tick; then the same ticks with the one-warp-per-agent k_tail, bit for bit."""
     L = f110._native.lib()
-    L.f110_debug_set_tail(-2)                      # force k_tail2 (by default it takes over from 24576 agents on)
+    L.f110_debug_set_tail(-2)                      # k_tail2 (the default for 2 <= A <= 4)
     try:
         n_col, n_occ = _rollout_vs_oracle(f110, dev, example_map, N=20, A=A, B=1080, T=50, gap=gap, seed=3100 + 10 * A + gap,
                                           all_tick=True)

@@ -30,7 +30,7 @@ import f1tenth_gym_b200 as f110   # noqa: E402
 from f1tenth_gym_b200 import _native as nat   # noqa: E402
 
 
-def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8):
+def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8, tail2=(256, 64)):
     w = bench.WORKLOADS[workload]
     N, A, B = w['num_envs'], w['num_agents'], w['num_beams']
     NA = N * A
@@ -40,6 +40,7 @@ def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8):
     L.f110_debug_set_dyn(int(dyn[0]), int(dyn[1]))
     L.f110_debug_set_pdl(int(pdl))
     L.f110_debug_set_tail(int(tail))
+    L.f110_debug_set_tail2(int(tail2[0]), int(tail2[1]))
     sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, bench.SEED, num_envs=N, num_beams=B, device=dev)
     sim.set_map(f110.maps.resolve_map_path('example_map'), '.png')
     wp_np = f110.maps.load_waypoints()
@@ -82,7 +83,7 @@ def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8):
         ev0[t].record(); sim.replay(); ev1[t].record()
     torch.cuda.synchronize(dev)
     tick_us = 1e3 * float(np.median([a.elapsed_time(b) for a, b in zip(ev0, ev1)]))
-    return {'workload': workload, 'variant': variant, 'chunk': chunk, 'dyn': list(dyn), 'pdl': pdl, 'tail_minb': tail, 'dyn_us': 1e3 * kms[0], 'march_us': 1e3 * kms[1],
+    return {'workload': workload, 'variant': variant, 'chunk': chunk, 'dyn': list(dyn), 'pdl': pdl, 'tail_minb': tail, 'tail2': list(tail2), 'dyn_us': 1e3 * kms[0], 'march_us': 1e3 * kms[1],
             'tail_us': 1e3 * kms[2], 'tick_graph_us': tick_us, 'agent_steps_per_s': NA / (tick_us * 1e-6),
             'hash': h.hexdigest()[:16]}
 
@@ -95,6 +96,7 @@ def main():
     ap.add_argument('--dyn', default='50:4', help='static_pct:ahead[,static_pct:ahead...] for the dynamic-tail variants 40/41')
     ap.add_argument('--pdl', default='0')
     ap.add_argument('--tail', default='8', help='k_tail register budget: 4 (128 regs), 5 (96), 8 (64); -1 = always k_tail, -2 = always the two-phase k_tail2')
+    ap.add_argument('--tail2', default='256:64', help='k_tail2 block shape threads:agents[,threads:agents...]')
     ap.add_argument('--ticks', type=int, default=40)
     ap.add_argument('--repeat', type=int, default=2)
     args = ap.parse_args()
@@ -107,10 +109,12 @@ def main():
                     for dy in (args.dyn.split(',') if v in (0, 40, 41, 42) else ['50:4']):
                         for pdl in [int(x) for x in args.pdl.split(',')]:
                             for tl in [int(x) for x in args.tail.split(',')]:
-                                r = run(wl, v, args.ticks, dev, ch, tuple(int(x) for x in dy.split(':')), pdl, tl)
-                                r['rep'] = rep
-                                rows.append(r)
-                                print(json.dumps(r), flush=True)
+                                for t2 in args.tail2.split(','):
+                                    r = run(wl, v, args.ticks, dev, ch, tuple(int(x) for x in dy.split(':')), pdl, tl,
+                                            tuple(int(x) for x in t2.split(':')))
+                                    r['rep'] = rep
+                                    rows.append(r)
+                                    print(json.dumps(r), flush=True)
         hs = {r['hash'] for r in rows if r['workload'] == wl}
         print(json.dumps({'workload': wl, 'identical_results_across_variants': len(hs) == 1}), flush=True)
 

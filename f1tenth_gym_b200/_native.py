@@ -100,6 +100,7 @@ DEBUG_SIGNATURES = {
     'f110_debug_set_variant': (None, [C.c_int]),
     'f110_debug_set_chunk': (None, [C.c_int]),
     'f110_debug_set_dyn': (None, [C.c_int, C.c_int]),
+    'f110_debug_set_ipt': (None, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'f110_debug_set_pdl': (None, [C.c_int]),
     'f110_debug_set_tail': (None, [C.c_int]),
     'f110_debug_set_tail2': (None, [C.c_int, C.c_int]),

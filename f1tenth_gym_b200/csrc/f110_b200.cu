@@ -983,6 +983,7 @@ static int g_variant = -1, g_chunk = -1;
 // the rest in runs from one global counter, g_dyn_ahead runs ahead of their use.  50 % / 4 is the measured optimum (cfg3 march
 // 419 -> 407 us, cfg2x2 116 -> 113.6, cfg2 68.5 -> 68.1; profiles/r2/ab_march_11..13_*.jsonl): the default of variant 0.
 static int g_dyn_pct = 50, g_dyn_ahead = 4;
+static int g_ipt[4] = {-1, -1, -1, 255};  // log2(entries per ticket): very heavy, heavy, light runs, dynamic tail (255 = by the class it starts in); -1 = by queue length
 static int rm_variant() {
     if (g_variant < 0) {
         const char *e = getenv("F110_MARCH_VARIANT");
@@ -1069,12 +1070,12 @@ static bool clusters_fit(K kernel, unsigned blocks, unsigned threads, unsigned c
     return (unsigned)n * cl >= blocks;
 }
 
-template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false, int PT = 512>
+template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false, int PT = 512, int IPT = 1>
 static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
     const bool pdl = g_pdl_this_step;
-    if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, PT, MINB, DYN>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
-    else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, PT, MINB, DYN>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
-    else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, PT, MINB, DYN>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, PT, MINB, DYN, 1, IPT>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, PT, MINB, DYN, 1, IPT>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, PT, MINB, DYN, 1, IPT>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
 }
 static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool cells, bool coded, bool occ3, bool layered,
                         bool noise, bool count, bool dyn, cudaStream_t st) {
@@ -1098,7 +1099,7 @@ static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool
     // cfg5_2160 819 -> 761, cfg2x2 120.2 -> 116.2 -- and lose when it does not: cfg2 (470 items per big block) 68.2 -> 70.5 us
     // (profiles/r2/ab_march_7_*.jsonl, ab_march_8_*.jsonl).  Variant 60 / 61 / 66 force 2 x 1024 / 8 x 256 / 4 x 512.
     const int v = rm_variant();
-    const bool big = (v == 60) || (v != 61 && v != 66 && v != 21 && v != 22 && !dyn && !coded && !occ3 &&
+    const bool big = (v == 60) || (v != 61 && v != 66 && v != 44 && v != 21 && v != 22 && !dyn && !coded && !occ3 &&
                                    (unsigned long long)mq.items >= 700ull * 2ull * (unsigned long long)sms);
     if (big && !coded) {
         if (!cells && layered) launch_lean_t<0, false, true, 2, false, 1024>(q, mq, sms * 2u, noise, count, st);
@@ -1108,13 +1109,23 @@ static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool
         return;
     }
     if (cells && !layered && !coded && v == 61) { launch_lean_t<0, true, false, 8, false, 256>(q, mq, sms * 8u, noise, count, st); return; }
+    // two queue entries per ticket (variant 43: dynamic, 4 x 512; 44: static, 4 x 512); needs runs of >= 2 entries
+    if (cells && !layered && !coded && mq.chunk_shift >= 1 && v == 43 && dyn) { launch_lean_t<0, true, false, 4, true, 512, 2>(q, mq, sms * 4u, noise, count, st); return; }
+    if (cells && !layered && !coded && mq.chunk_shift >= 2 && v == 45 && dyn) { launch_lean_t<0, true, false, 4, true, 512, 4>(q, mq, sms * 4u, noise, count, st); return; }
+    if (cells && !layered && !coded && mq.chunk_shift >= 1 && v == 44) { launch_lean_t<0, true, false, 4, false, 512, 2>(q, mq, sms * 4u, noise, count, st); return; }
     if (dyn && cells && !layered && !coded && v == 42) { launch_lean_t<0, true, false, 2, true, 1024>(q, mq, sms * 2u, noise, count, st); return; }
     if (dyn && cells && !layered && !coded) {
         if (occ3) launch_lean_t<0, true, false, 3, true>(q, mq, sms * 3u, noise, count, st);
-        else launch_lean_t<0, true, false, 4, true>(q, mq, sms * 4u, noise, count, st);
+        else if (v == 40) launch_lean_t<0, true, false, 4, true>(q, mq, sms * 4u, noise, count, st);       // one entry per ticket, compile-time
+        // Long queues (>= 72 entries per warp: cfg3, the beam sweep): four entries per ticket throughout, fixed at compile time --
+        // cfg3 march 368 us against 378 with the very heavy runs dealt one or two entries at a time, 407 with one entry per
+        // ticket everywhere.  Shorter queues: ticket size by the class of the run (dyn_queue_position_zoned), which is what
+        // keeps four very heavy entries from landing on one warp (uniform 4: cfg2x2 139 us instead of 112, cfg2 122 instead of 68).
+        else if (mq.uniform_ipt4 && v == 0) launch_lean_t<0, true, false, 4, true, 512, 4>(q, mq, sms * 4u, noise, count, st);
+        else launch_lean_t<0, true, false, 4, true, 512, 0>(q, mq, sms * 4u, noise, count, st);
         return;
     }
-    if (dyn && !cells && !layered) { launch_lean_t<0, false, false, 4, true>(q, mq, sms * 4u, noise, count, st); return; }
+    if (dyn && !cells && !layered) { launch_lean_t<0, false, false, 4, true, 512, 0>(q, mq, sms * 4u, noise, count, st); return; }
     if (!cells && layered) launch_lean_t<0, false, true, 4>(q, mq, sms * 4u, noise, count, st);
     else if (!cells) launch_lean_t<0, false, false, 4>(q, mq, sms * 4u, noise, count, st);
     else if (layered) launch_lean_t<0, true, true, 4>(q, mq, sms * 4u, noise, count, st);
@@ -1203,6 +1214,12 @@ void f110_debug_set_variant(int variant) { g_variant = variant < 0 ? 0 : variant
 void f110_debug_set_dyn(int static_pct, int ahead) {
     g_dyn_pct = static_pct < 0 ? 0 : (static_pct > 100 ? 100 : static_pct);
     g_dyn_ahead = ahead < 1 ? 1 : (ahead > 8 ? 8 : ahead);
+}
+/* log2(queue entries per ticket) for runs of very heavy / heavy / light entries and for the dynamic tail of the default launch
+ * (dyn_tail < 0: by the class the tail starts in) */
+void f110_debug_set_ipt(int very_heavy, int heavy, int light, int dyn_tail) {
+    const int v[4] = {very_heavy, heavy, light, dyn_tail};
+    for (int z = 0; z < 4; z++) g_ipt[z] = (v[z] < 0 || v[z] > 3) ? (z == 3 ? 255 : -1) : v[z];
 }
 void f110_debug_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 void f110_debug_set_tail2(int threads, int agents) {
@@ -1332,7 +1349,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
         const int bpa = (beams->num_beams + 63) / 64;
         if (bpa > 65000) return F110_ERR_INVALID;
         const bool noise = sim->noise_std > 0.0, count = sim->lookup_counter != nullptr;
-        MarchQueue mq;
+        MarchQueue mq = {};
         if (queued) {
             mq.cost = sim->march_cost; mq.order = sim->march_order; mq.count = sim->march_count;
             mq.ipa = (unsigned)sim->march_ipa; mq.items = (unsigned)NA * mq.ipa;
@@ -1346,6 +1363,22 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                 const unsigned blocks = (unsigned)num_sms() * (big_blocks ? 2u : 4u);
                 mq.dyn_ahead = (unsigned)g_dyn_ahead;
                 mq.static_runs = (unsigned)((unsigned long long)runs * (unsigned)g_dyn_pct / 100ull / blocks);
+                // entries per ticket by queue class (k_march_lean<IPT = 0>)
+                unsigned sh[4];
+                // (at least two tickets per run: with one, the 16 warps of a block could hold tickets of 16 runs at once and
+                // the claim for run r + 16 could overwrite the ring slot of run r before it is read)
+                const unsigned sh_max = mq.chunk_shift > 0u ? mq.chunk_shift - 1u : 0u;
+                // queue entries per warp of the launch: one entry per ticket for the very heavy runs, four for the light ones, and
+                // for the heavy runs two on a short queue, four on a longer one (cfg2: 68.3 us with 0:1:2, 69.8 with 0:2:2;
+                // n12288a1 and cfg2x2: 155.9 / 112.0 and 155.1 / 111.7; profiles/r2/ab_march_23_*.jsonl)
+                const unsigned per_warp = mq.items / (blocks * 16u);
+                const int dflt[4] = {0, per_warp >= 27u ? 2 : 1, 2, 255};
+                for (int z = 0; z < 4; z++) {
+                    const int want = g_ipt[z] < 0 ? dflt[z] : g_ipt[z];
+                    sh[z] = (z == 3 && want == 255) ? 255u : std::min((unsigned)want, sh_max);
+                }
+                mq.uniform_ipt4 = (per_warp >= 72u && g_ipt[0] < 0 && g_ipt[1] < 0 && g_ipt[2] < 0 && mq.chunk_shift >= 3u) ? 1u : 0u;
+                mq.ipt_shifts = sh[0] | (sh[1] << 8) | (sh[2] << 16) | (sh[3] << 24);
             }
         }
         if (lean) {
@@ -1388,7 +1421,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                 if ((rc = launch_tile(t, map, tile_sz, (unsigned)num_sms(), noise, count, st))) return rc;
             } else
             launch_lean(q, mq, (unsigned)num_sms(), cell_units, lcoded, occ3, layered, noise, count,
-                        /* dynamic queue tail: */ (variant == 0 || variant == 40 || variant == 41 || variant == 42) && !layered &&
+                        /* dynamic queue tail: */ (variant == 0 || variant == 40 || variant == 41 || variant == 42 || variant == 43 || variant == 45) && !layered &&
                             mq.static_runs >= mq.dyn_ahead, st);
         } else if (queued) {
             const unsigned blocks = (unsigned)num_sms() * 4u;

@@ -116,39 +116,80 @@ __device__ __noinline__ double redo_beam_cells(const double *__restrict__ table,
 //     2 x 1024 shape's 419; 85 % static loses, 10-30 % is 1-2 % behind): the static half keeps the head of the queue -- the
 //     heavy items -- free of claim latency, the dynamic half evens out the blocks.
 #define F110_DYN_RING 16u
-__device__ __noinline__ unsigned dyn_queue_position(unsigned k, bool elected, unsigned cs, unsigned static_runs, unsigned dyn_ahead,
-                                                    unsigned *claim, unsigned *s_run, unsigned *s_seq, unsigned qstride,
-                                                    unsigned qbase, unsigned nblocks) {
-    const unsigned r = k >> cs, idx = k & ((1u << cs) - 1u);
+// common tail of the two ticket -> queue position functions: (local run r, first entry idx of the ticket inside the run,
+// log2 entries of the ticket) -> position | (entries - 1) << 29
+__device__ __forceinline__ unsigned dyn_claim_and_locate(unsigned r, unsigned idx, unsigned sh, bool elected, unsigned cs,
+                                                         unsigned static_runs, unsigned dyn_ahead, unsigned *claim, unsigned *s_run,
+                                                         unsigned *s_seq, unsigned qstride, unsigned qbase, unsigned nblocks) {
+    const unsigned nsub1 = ((1u << sh) - 1u) << 29;
     if (idx == 0u && elected && r + dyn_ahead >= static_runs) {
         // first ticket of run r: claim the dynamic run that local run r + dyn_ahead will use
         const unsigned g = atomicAdd(claim, 1u);
         const unsigned nb = (r + dyn_ahead) & (F110_DYN_RING - 1u);
-        ((volatile unsigned *)s_run)[nb] = static_runs * nblocks + g;
+        // (the ring words are only touched with atomics: a flag hand-off between warps without a barrier, which is what it is,
+        // and compute-sanitizer's racecheck accepts it as such)
+        atomicExch(s_run + nb, static_runs * nblocks + g);
         __threadfence_block();
-        ((volatile unsigned *)s_seq)[nb] = r + dyn_ahead;
+        atomicExch(s_seq + nb, r + dyn_ahead);
     }
-    if (r < static_runs) return r * qstride + qbase + idx;
+    if (r < static_runs) return (r * qstride + qbase + idx) | nsub1;
     const unsigned buf = r & (F110_DYN_RING - 1u);
-    unsigned sq;
-    while ((sq = ((volatile unsigned *)s_seq)[buf]) != r) {
-        // a ring slot is reused 16 runs (>= 64 tickets) later: a warp cannot fall that far behind between drawing its ticket
-        // and reading the slot; if it ever did, stop loudly instead of marching the wrong items
-        if (sq != 0xFFFFFFFFu && sq > r) __trap();
+    unsigned run = 0u;
+    if (elected) {      // one lane polls the slot (32 lanes would be 32 serialized atomics on one word)
+        unsigned sq;
+        while ((sq = atomicOr(s_seq + buf, 0u)) != r) {
+            // a ring slot is reused 16 runs (>= 32 tickets: the host keeps at least two tickets per run) later: a warp cannot fall
+            // that far behind between drawing its ticket and reading the slot; if it ever did, stop loudly instead of marching the
+            // wrong items
+            if (sq != 0xFFFFFFFFu && sq > r) __trap();
+        }
+        __threadfence_block();
+        run = atomicOr(s_run + buf, 0u);
     }
-    return (((volatile unsigned *)s_run)[buf] << cs) + idx;
+    run = __shfl_sync(0xffffffffu, run, __ffs(__ballot_sync(0xffffffffu, elected)) - 1);
+    return ((run << cs) + idx) | nsub1;
+}
+// every ticket covers 2^sh consecutive queue entries (a run of 2^cs entries is 2^(cs - sh) tickets)
+__device__ __noinline__ unsigned dyn_queue_position(unsigned k, bool elected, unsigned cs, unsigned static_runs, unsigned dyn_ahead,
+                                                    unsigned *claim, unsigned *s_run, unsigned *s_seq, unsigned qstride,
+                                                    unsigned qbase, unsigned nblocks, unsigned sh) {
+    const unsigned r = k >> (cs - sh), idx = (k & ((1u << (cs - sh)) - 1u)) << sh;
+    return dyn_claim_and_locate(r, idx, sh, elected, cs, static_runs, dyn_ahead, claim, s_run, s_seq, qstride, qbase, nblocks);
+}
+// Ticket size by the class of the run (k_march_lean<IPT = 0>).  The queue holds the very heavy entries first, then the heavy,
+// then the light ones: a ticket of four consecutive VERY HEAVY entries puts four of the longest marches of the launch on one
+// warp, one after the other -- a constant ~30 us on the critical path at every batch size (ab_march_21/22: 4 entries per ticket
+// won 10 % at cfg3 and lost 25 % at cfg2x2) -- while for the light entries the pop and this call are a large part of the work.
+// zone[] (shared memory, written by thread 0 before the first pop): ticket bounds T1 <= T2 <= T3 of the block's static runs
+// that start in the very heavy / heavy / light part of the queue, the run counts rA, rAB behind them, and the four shifts
+// (very heavy | heavy << 8 | light << 16 | dynamic tail << 24).
+__device__ __noinline__ unsigned dyn_queue_position_zoned(unsigned k, bool elected, unsigned cs, unsigned static_runs,
+                                                          unsigned dyn_ahead, unsigned *claim, unsigned *s_run, unsigned *s_seq,
+                                                          unsigned qstride, unsigned qbase, unsigned nblocks, const unsigned *zone) {
+    const unsigned shifts = zone[5];
+    unsigned sh, r0;
+    if (k < zone[0]) { sh = shifts & 255u; r0 = 0u; }
+    else if (k < zone[1]) { sh = (shifts >> 8) & 255u; r0 = zone[3]; k -= zone[0]; }
+    else if (k < zone[2]) { sh = (shifts >> 16) & 255u; r0 = zone[4]; k -= zone[1]; }
+    else { sh = shifts >> 24; r0 = static_runs; k -= zone[2]; }
+    const unsigned r = r0 + (k >> (cs - sh)), idx = (k & ((1u << (cs - sh)) - 1u)) << sh;
+    return dyn_claim_and_locate(r, idx, sh, elected, cs, static_runs, dyn_ahead, claim, s_run, s_seq, qstride, qbase, nblocks);
 }
 // CL > 1: the kernel is launched in thread-block clusters of CL CTAs that share ONE ticket counter (the shared-memory word of
 // the cluster's rank-0 CTA, popped through distributed shared memory: mapa + atom.shared::cluster).  The queue is then dealt
 // statically to the CLUSTERS and handed out dynamically inside each: a pool of CL x PT/32 warps on several SMs of one GPC
 // instead of PT/32 warps on one SM, which evens out the finishing times without the global atomics that made the fully
 // dynamic queue lose (profiles/r2/README.md).
-template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB, bool DYN = false, int CL = 1>
+// IPT: queue entries per ticket (1, 2 or 4; 0 = by the class of the run, mq.ipt_shifts, dynamic queue only).  With 2, a warp that
+// pops the block's counter marches two consecutive entries of its run before it pops again: the pop, the queue arithmetic and
+// the dynamic-queue call are paid once per 64 beams (profiles/r2/ab_march_19..23_*.jsonl).
+template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB, bool DYN = false, int CL = 1, int IPT = 1>
 __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
     __shared__ unsigned s_run[DYN ? F110_DYN_RING : 1u], s_seq[DYN ? F110_DYN_RING : 1u];
     if (DYN && threadIdx.x < F110_DYN_RING) s_seq[threadIdx.x] = 0xFFFFFFFFu;
     __shared__ double s_lut[TABLE == 1 ? 256 : 1];
+    __shared__ unsigned s_zone[(DYN && IPT == 0) ? 6 : 1];
     if (threadIdx.x == 0) s_next = 0u;
     if (TABLE == 1)
         for (unsigned t = threadIdx.x; t < 256u; t += PT) s_lut[t] = p.lut[t];
@@ -156,6 +197,27 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
     // kernel reads what k_dynamics wrote (queue, per-agent records).
     pdl_wait();
     pdl_launch_dependents();
+    if (DYN && IPT == 0 && threadIdx.x == 0) {
+        // ticket sizes by queue class (dyn_queue_position_zoned).  Static run r of this block starts at queue entry
+        // (r * gridDim.x + blockIdx.x) << cs: count the runs that start below each class boundary.
+        const unsigned zA = min(mq.count[0], mq.items), zAB = zA + min(mq.count[1], mq.items);
+        const unsigned zcs = mq.chunk_shift, sr = mq.static_runs;
+        const unsigned gA = (zA + (1u << zcs) - 1u) >> zcs, gAB = (zAB + (1u << zcs) - 1u) >> zcs;
+        const unsigned rA = gA > blockIdx.x ? min((gA - blockIdx.x + gridDim.x - 1u) / gridDim.x, sr) : 0u;
+        const unsigned rAB = gAB > blockIdx.x ? min((gAB - blockIdx.x + gridDim.x - 1u) / gridDim.x, sr) : 0u;
+        const unsigned shA = mq.ipt_shifts & 255u, shB = (mq.ipt_shifts >> 8) & 255u, shC = (mq.ipt_shifts >> 16) & 255u;
+        unsigned shD = mq.ipt_shifts >> 24;
+        if (shD == 255u) {      // by the class the dynamic tail starts in
+            const unsigned long long d0 = ((unsigned long long)sr * gridDim.x) << zcs;
+            shD = d0 < zA ? shA : d0 < zAB ? shB : shC;
+        }
+        s_zone[0] = rA << (zcs - shA);
+        s_zone[1] = s_zone[0] + ((rAB - rA) << (zcs - shB));
+        s_zone[2] = s_zone[1] + ((sr - rAB) << (zcs - shC));
+        s_zone[3] = rA;
+        s_zone[4] = rAB;
+        s_zone[5] = (mq.ipt_shifts & 0xFFFFFFu) | (shD << 24);
+    }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nA = min(mq.count[0], mq.items), nB = min(mq.count[1], mq.items);
@@ -182,16 +244,27 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
             asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
                          : "+r"(k), "=r"(leader) : "r"(s_next_addr) : "memory");
         k = __shfl_sync(0xffffffffu, k, leader);
-        unsigned q;
+        unsigned q, nsub = (unsigned)IPT;
         if (DYN) {
             // out of line: inlined, the ring logic costs the whole item path its register allocation (ncu: 55.4 M instead of
             // 43.6 M warp-instructions per launch at cfg2 -- the clamp and the store of every beam grew)
-            q = dyn_queue_position(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride, qbase,
-                                   gridDim.x);
+            if (IPT == 0) {
+                q = dyn_queue_position_zoned(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride,
+                                             qbase, gridDim.x, s_zone);
+                nsub = (q >> 29) + 1u;
+            } else
+                q = dyn_queue_position(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride, qbase,
+                                       gridDim.x, IPT == 4 ? 2u : IPT == 2 ? 1u : 0u);
+            q &= 0x1FFFFFFFu;
         } else {
-            q = (k >> cs) * qstride + qbase + (k & qmask);
+            if (IPT == 4) q = (k >> (cs - 2u)) * qstride + qbase + ((k & (qmask >> 2)) << 2);
+            else if (IPT == 2) q = (k >> (cs - 1u)) * qstride + qbase + ((k & (qmask >> 1)) << 1);
+            else q = (k >> cs) * qstride + qbase + (k & qmask);
         }
         if (q >= total) break;
+#pragma unroll 1
+        for (unsigned sub = 0; sub < nsub; sub++, q++) {
+        if (IPT != 1 && q >= total) break;
         const unsigned it = mq.order[(q < nA) ? q : (q < nAB) ? (mq.items + (q - nA)) : (2u * mq.items + (q - nAB))];
         const unsigned a = it >> 8;
         const int i = (int)((it & 255u) * 32u + lane);
@@ -278,6 +351,7 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
         if (COUNT) looks += n;
         const unsigned mx = __reduce_max_sync(0xffffffffu, n);
         if (lane == 0) mq.cost[it] = mx;
+        }
     }
     if (COUNT) {
         const unsigned nsum = __reduce_add_sync(0xffffffffu, looks);

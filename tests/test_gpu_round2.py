@@ -202,7 +202,7 @@ def test_metre_march_variants_vs_oracle(f110, dev, variant, name, v):
     assert sim.lookups() == sum(o.nlook for o in osims)
 
 
-@pytest.mark.parametrize('v', [60, 61, 62, 63, 64, 65, 66])
+@pytest.mark.parametrize('v', [60, 61, 62, 63, 64, 65, 66, 43, 44])
 def test_block_shape_and_cluster_variants_bit_identical(f110, dev, example_map, variant, v):
     """Block shapes (2 x 1024, 8 x 256 threads per SM) and the thread-block-cluster launches that share one ticket counter
     through distributed shared memory: same scans, state and collisions as the default launch, bit for bit."""
@@ -234,7 +234,7 @@ def test_dynamic_queue_large_batch(f110, dev, example_map, variant):
     poses = _start_poses(f110, rng, N, A)
     acts = np.stack([rng.uniform(-0.4189, 0.4189, (T, N, A)), rng.uniform(0, 8, (T, N, A))], axis=3)
     out = {}
-    for vv in (66, 0, 42):
+    for vv in (66, 0, 42, 43, 44):
         variant(vv)
         sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev, count_lookups=(vv != 42))
         sim.set_device_map(example_map)
@@ -245,6 +245,8 @@ def test_dynamic_queue_large_batch(f110, dev, example_map, variant):
         out[vv] = (cpu(sim.scans).copy(), cpu(sim.state).copy(), sim.lookups())
     assert np.array_equal(out[0][0], out[66][0]) and np.array_equal(out[0][1], out[66][1]) and out[0][2] == out[66][2]
     assert np.array_equal(out[42][0], out[66][0])
+    for vv in (43, 44):         # two queue entries per ticket
+        assert np.array_equal(out[vv][0], out[66][0]) and np.array_equal(out[vv][1], out[66][1]) and out[vv][2] == out[66][2]
     omap = _omap(example_map)
     for e in range(0, N, 97):
         o = oracle.OracleSim(omap, num_agents=A)
@@ -252,6 +254,39 @@ def test_dynamic_queue_large_batch(f110, dev, example_map, variant):
         for t in range(T):
             o.step(acts[t, e])
         assert np.array_equal(out[0][0][e], o.scans[0].astype(np.float32)), e
+
+
+@pytest.mark.parametrize('chunk', [3, 2, 4])
+def test_ticket_sizes_bit_identical(f110, dev, example_map, variant, chunk):
+    """The default launch lets a warp draw 1, 2, 4 or 8 consecutive queue entries per ticket, by the class of the run (very heavy /
+    heavy / light) and for the dynamic tail (forced here through f110_debug_set_ipt, with runs of 4, 8 and 16 entries): every
+    combination gives the scans, states and lookup count of the static launch, bit for bit."""
+    N, A, T = 2048, 1, 4
+    L = f110._native.lib()
+    rng = np.random.default_rng(7)
+    poses = _start_poses(f110, rng, N, A)
+    acts = np.stack([rng.uniform(-0.4189, 0.4189, (T, N, A)), rng.uniform(0, 8, (T, N, A))], axis=3)
+
+    def go(v, ipt):
+        variant(v)
+        L.f110_debug_set_ipt(*ipt)
+        sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev, count_lookups=True)
+        sim.set_device_map(example_map)
+        sim.reset(poses)
+        for t in range(T):
+            sim.tick(acts[t], env_level=False)
+        torch.cuda.synchronize()
+        return cpu(sim.scans).copy(), cpu(sim.state).copy(), sim.lookups()
+    try:
+        L.f110_debug_set_chunk(chunk)
+        ref = go(66, (-1, -1, -1, -1))
+        for ipt in [(-1, -1, -1, -1), (0, 0, 0, 0), (0, 1, 2, 0), (0, 1, 2, 1), (2, 1, 0, 2), (1, 1, 1, 1), (2, 2, 2, 2), (0, 1, 3, 3),
+                    (3, 3, 3, 3), (0, 2, 3, -1), (1, 0, 2, 0)]:
+            got = go(0, ipt)
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2], ipt
+    finally:
+        L.f110_debug_set_ipt(-1, -1, -1, -1)
+        L.f110_debug_set_chunk(3)
 
 
 @pytest.mark.parametrize('A,gap', [(2, 3), (3, 4), (4, 3), (2, 23)])

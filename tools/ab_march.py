@@ -22,6 +22,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import re
+
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
@@ -30,8 +32,9 @@ import f1tenth_gym_b200 as f110   # noqa: E402
 from f1tenth_gym_b200 import _native as nat   # noqa: E402
 
 
-def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8, tail2=(256, 64)):
-    w = bench.WORKLOADS[workload]
+def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8, tail2=(256, 64), ipt=(-1, -1, -1, -1)):
+    m = re.match(r'^n(\d+)a(\d+)(?:b(\d+))?$', workload)      # ad-hoc size: n<envs>a<agents>[b<beams>]
+    w = dict(num_envs=int(m.group(1)), num_agents=int(m.group(2)), num_beams=int(m.group(3) or 1080)) if m else bench.WORKLOADS[workload]
     N, A, B = w['num_envs'], w['num_agents'], w['num_beams']
     NA = N * A
     L = nat.lib()
@@ -39,6 +42,7 @@ def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8, tail
     L.f110_debug_set_chunk(int(chunk))
     L.f110_debug_set_dyn(int(dyn[0]), int(dyn[1]))
     L.f110_debug_set_pdl(int(pdl))
+    L.f110_debug_set_ipt(*[int(x) for x in ipt])
     L.f110_debug_set_tail(int(tail))
     L.f110_debug_set_tail2(int(tail2[0]), int(tail2[1]))
     sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, bench.SEED, num_envs=N, num_beams=B, device=dev)
@@ -83,7 +87,7 @@ def run(workload, variant, ticks, dev, chunk=3, dyn=(50, 4), pdl=0, tail=8, tail
         ev0[t].record(); sim.replay(); ev1[t].record()
     torch.cuda.synchronize(dev)
     tick_us = 1e3 * float(np.median([a.elapsed_time(b) for a, b in zip(ev0, ev1)]))
-    return {'workload': workload, 'variant': variant, 'chunk': chunk, 'dyn': list(dyn), 'pdl': pdl, 'tail_minb': tail, 'tail2': list(tail2), 'dyn_us': 1e3 * kms[0], 'march_us': 1e3 * kms[1],
+    return {'workload': workload, 'variant': variant, 'chunk': chunk, 'dyn': list(dyn), 'pdl': pdl, 'tail_minb': tail, 'tail2': list(tail2), 'ipt': list(ipt), 'dyn_us': 1e3 * kms[0], 'march_us': 1e3 * kms[1],
             'tail_us': 1e3 * kms[2], 'tick_graph_us': tick_us, 'agent_steps_per_s': NA / (tick_us * 1e-6),
             'hash': h.hexdigest()[:16]}
 
@@ -97,6 +101,7 @@ def main():
     ap.add_argument('--pdl', default='0')
     ap.add_argument('--tail', default='8', help='k_tail register budget: 4 (128 regs), 5 (96), 8 (64); -1 = always k_tail, -2 = always the two-phase k_tail2')
     ap.add_argument('--tail2', default='256:64', help='k_tail2 block shape threads:agents[,threads:agents...]')
+    ap.add_argument('--ipt', default='-1:-1:-1:-1', help='log2(entries per ticket) veryheavy:heavy:light:dyntail[,...] for variant 0; -1 = default (0:1:2:by class)')
     ap.add_argument('--ticks', type=int, default=40)
     ap.add_argument('--repeat', type=int, default=2)
     args = ap.parse_args()
@@ -106,15 +111,16 @@ def main():
         for rep in range(args.repeat):
             for v in [int(x) for x in args.variants.split(',')]:
                 for ch in [int(x) for x in args.chunks.split(',')]:
-                    for dy in (args.dyn.split(',') if v in (0, 40, 41, 42) else ['50:4']):
+                    for dy in (args.dyn.split(',') if v in (0, 40, 41, 42, 43, 45) else ['50:4']):
                         for pdl in [int(x) for x in args.pdl.split(',')]:
                             for tl in [int(x) for x in args.tail.split(',')]:
                                 for t2 in args.tail2.split(','):
-                                    r = run(wl, v, args.ticks, dev, ch, tuple(int(x) for x in dy.split(':')), pdl, tl,
-                                            tuple(int(x) for x in t2.split(':')))
-                                    r['rep'] = rep
-                                    rows.append(r)
-                                    print(json.dumps(r), flush=True)
+                                    for ip in (args.ipt.split(',') if v == 0 else ['-1:-1:-1:-1']):
+                                        r = run(wl, v, args.ticks, dev, ch, tuple(int(x) for x in dy.split(':')), pdl, tl,
+                                                tuple(int(x) for x in t2.split(':')), tuple(int(x) for x in ip.split(':')))
+                                        r['rep'] = rep
+                                        rows.append(r)
+                                        print(json.dumps(r), flush=True)
         hs = {r['hash'] for r in rows if r['workload'] == wl}
         print(json.dumps({'workload': wl, 'identical_results_across_variants': len(hs) == 1}), flush=True)
 

@@ -1070,12 +1070,12 @@ static bool clusters_fit(K kernel, unsigned blocks, unsigned threads, unsigned c
     return (unsigned)n * cl >= blocks;
 }
 
-template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false, int PT = 512, int IPT = 1>
+template <int TABLE, bool CELLS, bool LAYERED, int MINB, bool DYN = false, int PT = 512, int IPT = 1, int RING = 0>
 static void launch_lean_t(const LeanK &q, const MarchQueue &mq, unsigned blocks, bool noise, bool count, cudaStream_t st) {
     const bool pdl = g_pdl_this_step;
-    if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, PT, MINB, DYN, 1, IPT>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
-    else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, PT, MINB, DYN, 1, IPT>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
-    else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, PT, MINB, DYN, 1, IPT>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    if (count) launch_k(k_march_lean<TABLE, false, true, CELLS, LAYERED, PT, MINB, DYN, 1, IPT, RING>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    else if (noise) launch_k(k_march_lean<TABLE, true, false, CELLS, LAYERED, PT, MINB, DYN, 1, IPT, RING>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
+    else launch_k(k_march_lean<TABLE, false, false, CELLS, LAYERED, PT, MINB, DYN, 1, IPT, RING>, dim3(blocks), dim3(PT), 0, st, pdl, q, mq);
 }
 static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool cells, bool coded, bool occ3, bool layered,
                         bool noise, bool count, bool dyn, cudaStream_t st) {
@@ -1113,6 +1113,19 @@ static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool
     if (cells && !layered && !coded && mq.chunk_shift >= 1 && v == 43 && dyn) { launch_lean_t<0, true, false, 4, true, 512, 2>(q, mq, sms * 4u, noise, count, st); return; }
     if (cells && !layered && !coded && mq.chunk_shift >= 2 && v == 45 && dyn) { launch_lean_t<0, true, false, 4, true, 512, 4>(q, mq, sms * 4u, noise, count, st); return; }
     if (cells && !layered && !coded && mq.chunk_shift >= 1 && v == 44) { launch_lean_t<0, true, false, 4, false, 512, 2>(q, mq, sms * 4u, noise, count, st); return; }
+    // ring hand-off through shared atomics (81 / 83 / 85: 4 / 2 entries per ticket / by run class) and through st.release / ld.acquire
+    // (82 / 84 / 86)
+    if (dyn && cells && !layered && !coded && mq.chunk_shift >= 3) {
+        if (v == 81) { launch_lean_t<0, true, false, 4, true, 512, 4, 1>(q, mq, sms * 4u, noise, count, st); return; }
+        if (v == 82) { launch_lean_t<0, true, false, 4, true, 512, 4, 2>(q, mq, sms * 4u, noise, count, st); return; }
+        if (v == 83) { launch_lean_t<0, true, false, 4, true, 512, 2, 1>(q, mq, sms * 4u, noise, count, st); return; }
+        if (v == 84) { launch_lean_t<0, true, false, 4, true, 512, 2, 2>(q, mq, sms * 4u, noise, count, st); return; }
+        if (v == 85) { launch_lean_t<0, true, false, 4, true, 512, 0, 1>(q, mq, sms * 4u, noise, count, st); return; }
+        if (v == 86) { launch_lean_t<0, true, false, 4, true, 512, 0, 2>(q, mq, sms * 4u, noise, count, st); return; }
+    }
+    // 48 warps per SM (3 x 512 threads, 40 registers) with 4 / 2 entries per ticket
+    if (dyn && cells && !layered && !coded && mq.chunk_shift >= 3 && v == 57) { launch_lean_t<0, true, false, 3, true, 512, 4>(q, mq, sms * 3u, noise, count, st); return; }
+    if (dyn && cells && !layered && !coded && mq.chunk_shift >= 2 && v == 58) { launch_lean_t<0, true, false, 3, true, 512, 2>(q, mq, sms * 3u, noise, count, st); return; }
     if (dyn && cells && !layered && !coded && v == 42) { launch_lean_t<0, true, false, 2, true, 1024>(q, mq, sms * 2u, noise, count, st); return; }
     if (dyn && cells && !layered && !coded) {
         if (occ3) launch_lean_t<0, true, false, 3, true>(q, mq, sms * 3u, noise, count, st);
@@ -1121,11 +1134,15 @@ static void launch_lean(const LeanK &q, const MarchQueue &mq, unsigned sms, bool
         // cfg3 march 368 us against 378 with the very heavy runs dealt one or two entries at a time, 407 with one entry per
         // ticket everywhere.  Shorter queues: ticket size by the class of the run (dyn_queue_position_zoned), which is what
         // keeps four very heavy entries from landing on one warp (uniform 4: cfg2x2 139 us instead of 112, cfg2 122 instead of 68).
-        else if (mq.uniform_ipt4 && v == 0) launch_lean_t<0, true, false, 4, true, 512, 4>(q, mq, sms * 4u, noise, count, st);
-        else launch_lean_t<0, true, false, 4, true, 512, 0>(q, mq, sms * 4u, noise, count, st);
+        // Medium queues (27..72 entries per warp: cfg2x2, n12288a1): two entries per ticket (cfg2x2 109-110 us against 111 by class).
+        // The ring words go through st.release / ld.acquire (RING = 2; the volatile formulation times the same, the one in
+        // shared atomics that racecheck accepts costs 13 %: profiles/r2/ab_march_28_ring_handoff.jsonl).
+        else if (mq.uniform_ipt4 == 4u && v == 0) launch_lean_t<0, true, false, 4, true, 512, 4, 2>(q, mq, sms * 4u, noise, count, st);
+        else if (mq.uniform_ipt4 == 2u && v == 0) launch_lean_t<0, true, false, 4, true, 512, 2, 2>(q, mq, sms * 4u, noise, count, st);
+        else launch_lean_t<0, true, false, 4, true, 512, 0, 2>(q, mq, sms * 4u, noise, count, st);
         return;
     }
-    if (dyn && !cells && !layered) { launch_lean_t<0, false, false, 4, true, 512, 0>(q, mq, sms * 4u, noise, count, st); return; }
+    if (dyn && !cells && !layered) { launch_lean_t<0, false, false, 4, true, 512, 0, 2>(q, mq, sms * 4u, noise, count, st); return; }
     if (!cells && layered) launch_lean_t<0, false, true, 4>(q, mq, sms * 4u, noise, count, st);
     else if (!cells) launch_lean_t<0, false, false, 4>(q, mq, sms * 4u, noise, count, st);
     else if (layered) launch_lean_t<0, true, true, 4>(q, mq, sms * 4u, noise, count, st);
@@ -1360,7 +1377,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                 const unsigned runs = (mq.items + (1u << mq.chunk_shift) - 1u) >> mq.chunk_shift;
                 // (blocks of the lean launch: 2 per SM when the big shape is chosen -- same rule as launch_lean)
                 const bool big_blocks = (variant == 42);      // the dynamic default (variants 0 / 40 / 41) runs 4 x 512 threads per SM
-                const unsigned blocks = (unsigned)num_sms() * (big_blocks ? 2u : 4u);
+                const unsigned blocks = (unsigned)num_sms() * (big_blocks ? 2u : (variant == 41 || variant == 57 || variant == 58) ? 3u : 4u);
                 mq.dyn_ahead = (unsigned)g_dyn_ahead;
                 mq.static_runs = (unsigned)((unsigned long long)runs * (unsigned)g_dyn_pct / 100ull / blocks);
                 // entries per ticket by queue class (k_march_lean<IPT = 0>)
@@ -1377,7 +1394,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                     const int want = g_ipt[z] < 0 ? dflt[z] : g_ipt[z];
                     sh[z] = (z == 3 && want == 255) ? 255u : std::min((unsigned)want, sh_max);
                 }
-                mq.uniform_ipt4 = (per_warp >= 72u && g_ipt[0] < 0 && g_ipt[1] < 0 && g_ipt[2] < 0 && mq.chunk_shift >= 3u) ? 1u : 0u;
+                mq.uniform_ipt4 = (g_ipt[0] >= 0 || g_ipt[1] >= 0 || g_ipt[2] >= 0 || mq.chunk_shift < 3u) ? 0u : per_warp >= 72u ? 4u : per_warp >= 27u ? 2u : 0u;
                 mq.ipt_shifts = sh[0] | (sh[1] << 8) | (sh[2] << 16) | (sh[3] << 24);
             }
         }
@@ -1421,7 +1438,7 @@ static int step_impl(const f110_sim *sim, const f110_map *map, const f110_beams 
                 if ((rc = launch_tile(t, map, tile_sz, (unsigned)num_sms(), noise, count, st))) return rc;
             } else
             launch_lean(q, mq, (unsigned)num_sms(), cell_units, lcoded, occ3, layered, noise, count,
-                        /* dynamic queue tail: */ (variant == 0 || variant == 40 || variant == 41 || variant == 42 || variant == 43 || variant == 45) && !layered &&
+                        /* dynamic queue tail: */ (variant == 0 || variant == 40 || variant == 41 || variant == 42 || variant == 43 || variant == 45 || variant == 57 || variant == 58 || (variant >= 81 && variant <= 86)) && !layered &&
                             mq.static_runs >= mq.dyn_ahead, st);
         } else if (queued) {
             const unsigned blocks = (unsigned)num_sms() * 4u;

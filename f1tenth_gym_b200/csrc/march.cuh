@@ -94,7 +94,7 @@ struct MarchQueue {
     unsigned *claim;                        // global run counter of the dynamic queue tail (k_march_lean<DYN>), zeroed every tick
     unsigned static_runs;                   // DYN: runs per block that are dealt statically (>= dyn_ahead)
     unsigned dyn_ahead;                     // DYN: how many local runs ahead a dynamic run is claimed (1..8)
-    unsigned uniform_ipt4;                  // DYN: the queue is long enough for four entries per ticket throughout (host's choice)
+    unsigned uniform_ipt4;                  // DYN: 4 / 2 = the queue is long enough for that many entries per ticket throughout, 0 = ticket size by run class (host's choice)
     unsigned ipt_shifts;                    // DYN: log2(queue entries per ticket): very heavy | heavy << 8 | light << 16 | dynamic tail << 24 (255 = by class)
 };
 

@@ -118,6 +118,10 @@ __device__ __noinline__ double redo_beam_cells(const double *__restrict__ table,
 #define F110_DYN_RING 16u
 // common tail of the two ticket -> queue position functions: (local run r, first entry idx of the ticket inside the run,
 // log2 entries of the ticket) -> position | (entries - 1) << 29
+// RING: how the ring words are handed from the claiming warp to the reading warps -- 0: volatile stores and loads around a
+// __threadfence_block (every lane polls: a broadcast read); 1: shared-memory atomics, polled by the elected lane alone (32 lanes
+// would be 32 serialized atomics on one word) and broadcast by a shuffle; 2: st.release.cta / ld.acquire.cta.
+template <int RING>
 __device__ __forceinline__ unsigned dyn_claim_and_locate(unsigned r, unsigned idx, unsigned sh, bool elected, unsigned cs,
                                                          unsigned static_runs, unsigned dyn_ahead, unsigned *claim, unsigned *s_run,
                                                          unsigned *s_seq, unsigned qstride, unsigned qbase, unsigned nblocks) {
@@ -126,35 +130,54 @@ __device__ __forceinline__ unsigned dyn_claim_and_locate(unsigned r, unsigned id
         // first ticket of run r: claim the dynamic run that local run r + dyn_ahead will use
         const unsigned g = atomicAdd(claim, 1u);
         const unsigned nb = (r + dyn_ahead) & (F110_DYN_RING - 1u);
-        // (the ring words are only touched with atomics: a flag hand-off between warps without a barrier, which is what it is,
-        // and compute-sanitizer's racecheck accepts it as such)
-        atomicExch(s_run + nb, static_runs * nblocks + g);
-        __threadfence_block();
-        atomicExch(s_seq + nb, r + dyn_ahead);
+        if (RING == 1) {
+            atomicExch(s_run + nb, static_runs * nblocks + g);
+            __threadfence_block();
+            atomicExch(s_seq + nb, r + dyn_ahead);
+        } else if (RING == 2) {
+            asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(s_run + nb)), "r"(static_runs * nblocks + g) : "memory");
+            asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(s_seq + nb)), "r"(r + dyn_ahead) : "memory");
+        } else {
+            ((volatile unsigned *)s_run)[nb] = static_runs * nblocks + g;
+            __threadfence_block();
+            ((volatile unsigned *)s_seq)[nb] = r + dyn_ahead;
+        }
     }
     if (r < static_runs) return (r * qstride + qbase + idx) | nsub1;
     const unsigned buf = r & (F110_DYN_RING - 1u);
-    unsigned run = 0u;
-    if (elected) {      // one lane polls the slot (32 lanes would be 32 serialized atomics on one word)
-        unsigned sq;
-        while ((sq = atomicOr(s_seq + buf, 0u)) != r) {
-            // a ring slot is reused 16 runs (>= 32 tickets: the host keeps at least two tickets per run) later: a warp cannot fall
-            // that far behind between drawing its ticket and reading the slot; if it ever did, stop loudly instead of marching the
-            // wrong items
+    // a ring slot is reused 16 runs (>= 32 tickets: the host keeps at least two tickets per run) later: a warp cannot fall that far
+    // behind between drawing its ticket and reading the slot; if it ever did, stop loudly instead of marching the wrong items
+    unsigned run = 0u, sq;
+    if (RING == 1) {
+        if (elected) {
+            while ((sq = atomicOr(s_seq + buf, 0u)) != r)
+                if (sq != 0xFFFFFFFFu && sq > r) __trap();
+            __threadfence_block();
+            run = atomicOr(s_run + buf, 0u);
+        }
+        run = __shfl_sync(0xffffffffu, run, __ffs(__ballot_sync(0xffffffffu, elected)) - 1);
+    } else if (RING == 2) {
+        const unsigned a_seq = (unsigned)__cvta_generic_to_shared(s_seq + buf), a_run = (unsigned)__cvta_generic_to_shared(s_run + buf);
+        for (;;) {
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(sq) : "r"(a_seq) : "memory");
+            if (sq == r) break;
             if (sq != 0xFFFFFFFFu && sq > r) __trap();
         }
-        __threadfence_block();
-        run = atomicOr(s_run + buf, 0u);
+        asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(run) : "r"(a_run) : "memory");
+    } else {
+        while ((sq = ((volatile unsigned *)s_seq)[buf]) != r)
+            if (sq != 0xFFFFFFFFu && sq > r) __trap();
+        run = ((volatile unsigned *)s_run)[buf];
     }
-    run = __shfl_sync(0xffffffffu, run, __ffs(__ballot_sync(0xffffffffu, elected)) - 1);
     return ((run << cs) + idx) | nsub1;
 }
 // every ticket covers 2^sh consecutive queue entries (a run of 2^cs entries is 2^(cs - sh) tickets)
+template <int RING>
 __device__ __noinline__ unsigned dyn_queue_position(unsigned k, bool elected, unsigned cs, unsigned static_runs, unsigned dyn_ahead,
                                                     unsigned *claim, unsigned *s_run, unsigned *s_seq, unsigned qstride,
                                                     unsigned qbase, unsigned nblocks, unsigned sh) {
     const unsigned r = k >> (cs - sh), idx = (k & ((1u << (cs - sh)) - 1u)) << sh;
-    return dyn_claim_and_locate(r, idx, sh, elected, cs, static_runs, dyn_ahead, claim, s_run, s_seq, qstride, qbase, nblocks);
+    return dyn_claim_and_locate<RING>(r, idx, sh, elected, cs, static_runs, dyn_ahead, claim, s_run, s_seq, qstride, qbase, nblocks);
 }
 // Ticket size by the class of the run (k_march_lean<IPT = 0>).  The queue holds the very heavy entries first, then the heavy,
 // then the light ones: a ticket of four consecutive VERY HEAVY entries puts four of the longest marches of the launch on one
@@ -163,6 +186,7 @@ __device__ __noinline__ unsigned dyn_queue_position(unsigned k, bool elected, un
 // zone[] (shared memory, written by thread 0 before the first pop): ticket bounds T1 <= T2 <= T3 of the block's static runs
 // that start in the very heavy / heavy / light part of the queue, the run counts rA, rAB behind them, and the four shifts
 // (very heavy | heavy << 8 | light << 16 | dynamic tail << 24).
+template <int RING>
 __device__ __noinline__ unsigned dyn_queue_position_zoned(unsigned k, bool elected, unsigned cs, unsigned static_runs,
                                                           unsigned dyn_ahead, unsigned *claim, unsigned *s_run, unsigned *s_seq,
                                                           unsigned qstride, unsigned qbase, unsigned nblocks, const unsigned *zone) {
@@ -173,7 +197,7 @@ __device__ __noinline__ unsigned dyn_queue_position_zoned(unsigned k, bool elect
     else if (k < zone[2]) { sh = (shifts >> 16) & 255u; r0 = zone[4]; k -= zone[1]; }
     else { sh = shifts >> 24; r0 = static_runs; k -= zone[2]; }
     const unsigned r = r0 + (k >> (cs - sh)), idx = (k & ((1u << (cs - sh)) - 1u)) << sh;
-    return dyn_claim_and_locate(r, idx, sh, elected, cs, static_runs, dyn_ahead, claim, s_run, s_seq, qstride, qbase, nblocks);
+    return dyn_claim_and_locate<RING>(r, idx, sh, elected, cs, static_runs, dyn_ahead, claim, s_run, s_seq, qstride, qbase, nblocks);
 }
 // CL > 1: the kernel is launched in thread-block clusters of CL CTAs that share ONE ticket counter (the shared-memory word of
 // the cluster's rank-0 CTA, popped through distributed shared memory: mapa + atom.shared::cluster).  The queue is then dealt
@@ -183,7 +207,7 @@ __device__ __noinline__ unsigned dyn_queue_position_zoned(unsigned k, bool elect
 // IPT: queue entries per ticket (1, 2 or 4; 0 = by the class of the run, mq.ipt_shifts, dynamic queue only).  With 2, a warp that
 // pops the block's counter marches two consecutive entries of its run before it pops again: the pop, the queue arithmetic and
 // the dynamic-queue call are paid once per 64 beams (profiles/r2/ab_march_19..23_*.jsonl).
-template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB, bool DYN = false, int CL = 1, int IPT = 1>
+template <int TABLE, bool NOISE, bool COUNT, bool CELLS, bool LAYERED, int PT, int MINB, bool DYN = false, int CL = 1, int IPT = 1, int RING = 0>
 __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const MarchQueue mq) {
     __shared__ unsigned s_next;
     __shared__ unsigned s_run[DYN ? F110_DYN_RING : 1u], s_seq[DYN ? F110_DYN_RING : 1u];
@@ -249,11 +273,11 @@ __global__ void __launch_bounds__(PT, MINB) k_march_lean(const LeanK p, const Ma
             // out of line: inlined, the ring logic costs the whole item path its register allocation (ncu: 55.4 M instead of
             // 43.6 M warp-instructions per launch at cfg2 -- the clamp and the store of every beam grew)
             if (IPT == 0) {
-                q = dyn_queue_position_zoned(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride,
+                q = dyn_queue_position_zoned<RING>(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride,
                                              qbase, gridDim.x, s_zone);
                 nsub = (q >> 29) + 1u;
             } else
-                q = dyn_queue_position(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride, qbase,
+                q = dyn_queue_position<RING>(k, lane == leader, cs, mq.static_runs, mq.dyn_ahead, mq.claim, s_run, s_seq, qstride, qbase,
                                        gridDim.x, IPT == 4 ? 2u : IPT == 2 ? 1u : 0u);
             q &= 0x1FFFFFFFu;
         } else {

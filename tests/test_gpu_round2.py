@@ -234,7 +234,7 @@ def test_dynamic_queue_large_batch(f110, dev, example_map, variant):
     poses = _start_poses(f110, rng, N, A)
     acts = np.stack([rng.uniform(-0.4189, 0.4189, (T, N, A)), rng.uniform(0, 8, (T, N, A))], axis=3)
     out = {}
-    for vv in (66, 0, 42, 43, 44):
+    for vv in (66, 0, 42, 43, 44, 45, 57, 58, 81, 82, 83, 84, 85, 86):
         variant(vv)
         sim = f110.Simulator(f110.maps.DEFAULT_PARAMS, A, 1, num_envs=N, device=dev, count_lookups=(vv != 42))
         sim.set_device_map(example_map)
@@ -245,7 +245,7 @@ def test_dynamic_queue_large_batch(f110, dev, example_map, variant):
         out[vv] = (cpu(sim.scans).copy(), cpu(sim.state).copy(), sim.lookups())
     assert np.array_equal(out[0][0], out[66][0]) and np.array_equal(out[0][1], out[66][1]) and out[0][2] == out[66][2]
     assert np.array_equal(out[42][0], out[66][0])
-    for vv in (43, 44):         # two queue entries per ticket
+    for vv in (43, 44, 45, 57, 58, 81, 82, 83, 84, 85, 86):     # several entries per ticket, 48 warps per SM, the three ring hand-offs
         assert np.array_equal(out[vv][0], out[66][0]) and np.array_equal(out[vv][1], out[66][1]) and out[vv][2] == out[66][2]
     omap = _omap(example_map)
     for e in range(0, N, 97):

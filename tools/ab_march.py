@@ -111,7 +111,7 @@ def main():
         for rep in range(args.repeat):
             for v in [int(x) for x in args.variants.split(',')]:
                 for ch in [int(x) for x in args.chunks.split(',')]:
-                    for dy in (args.dyn.split(',') if v in (0, 40, 41, 42, 43, 45) else ['50:4']):
+                    for dy in (args.dyn.split(',') if v in (0, 40, 41, 42, 43, 45, 57, 58) or 81 <= v <= 86 else ['50:4']):
                         for pdl in [int(x) for x in args.pdl.split(',')]:
                             for tl in [int(x) for x in args.tail.split(',')]:
                                 for t2 in args.tail2.split(','):

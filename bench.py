@@ -522,7 +522,7 @@ def run_b200(args):
         for name in EXTRA_WORKLOADS:
             if name == args.workload:
                 continue
-            r = measure_workload(name, min(K, 100), min(max(W, 3), 10), Ke=40, prof_ticks=8, **common)
+            r = measure_workload(name, min(K, 100), min(max(W, 3), 10), Ke=120, prof_ticks=8, **common)
             extras[name] = {k: r[k] for k in ('value', 'ms_per_step', 'steps', 'warmup', 'e2e', 'roofline', 'num_envs_per_gpu',
                                               'num_agents', 'num_beams')}
 

@@ -1033,6 +1033,7 @@ static void launch_persistent(const MarchK &k, const MarchQueue &mq, unsigned bl
 static int g_pdl = 0;
 static int g_tail_minb = 8;
 static int g_tail2_threads = F110_TAIL2_THREADS, g_tail2_agents = 64;    // block shape of k_tail2 (f110_debug_set_tail2)
+static int g_tail2_forced = 0;                                            // agents per block forced exactly (debug setter, agents > 64 or < 0)
 static int g_tail2 = 1;          // 2 <= A <= 4: the two-phase k_tail2 (f110_debug_set_tail(-1) switches back to k_tail for the A/B)
 static thread_local bool g_pdl_this_step = false;     // set by step_impl: PDL only when no events are recorded between the kernels
 template <typename... KArgs, typename... Args>
@@ -1241,7 +1242,9 @@ void f110_debug_set_ipt(int very_heavy, int heavy, int light, int dyn_tail) {
 void f110_debug_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 void f110_debug_set_tail2(int threads, int agents) {
     g_tail2_threads = (threads >= 32 && threads <= F110_TAIL2_THREADS) ? (threads / 32) * 32 : F110_TAIL2_THREADS;
-    g_tail2_agents = (agents >= 4 && agents <= 64) ? agents : 64;
+    g_tail2_forced = (agents > 64 || agents < 0) ? 1 : 0;
+    if (agents < 0) agents = -agents;
+    g_tail2_agents = (agents >= 4 && agents <= 128) ? agents : 64;
 }
 void f110_debug_set_tail(int minb) {      // -1: k_tail always; -2 or a register budget: k_tail2 for 2 <= A <= 4 (the default)
     if (minb == -1) { g_tail2 = 0; g_tail_minb = 8; }
@@ -1481,13 +1484,32 @@ marched:
         // f110_step (no lap logic, no auto-reset) runs the same kernel with the env-level phase switched off
         // up to 64 agents per block, fewer when that would leave SMs without a block (cfg2x2: 4096 envs / 32 = 128 blocks lost
         // 4 us against 8 envs per block)
-        const int epb = max(1, min(g_tail2_agents / sim->num_agents, sim->num_envs / (4 * num_sms())));
-        const size_t smem = (size_t)epb * sim->num_agents * (sim->num_agents - 1) * sizeof(TailTask);
+        int epb = g_tail2_forced ? max(1, g_tail2_agents / sim->num_agents) : max(1, min(g_tail2_agents / sim->num_agents, sim->num_envs / (4 * num_sms())));
         AutoResetArgs no_ar;
         no_ar.start_poses = nullptr; no_ar.num_start = 0; no_ar.pose_gap = 0; no_ar.seed = 0; no_ar.tick_host = 0;
         const bool fused = tail && tail->fused;
         // big blocks (>= 48 agents) run 256 threads, small ones 128 (measured: 256:64 best at cfg3, 128:12 at cfg2x2)
-        const int t2 = (g_tail2_threads != F110_TAIL2_THREADS) ? g_tail2_threads : (epb * sim->num_agents >= 48 ? 256 : 128);
+        int t2 = (g_tail2_threads != F110_TAIL2_THREADS) ? g_tail2_threads : (epb * sim->num_agents >= 48 ? 256 : 128);
+        if (!g_tail2_forced && g_tail2_threads == F110_TAIL2_THREADS) {
+            // Whole waves.  With 80 registers an SM holds six 128-thread blocks (three of 256 threads); a grid of 1.37 waves (cfg3:
+            // 607 blocks of 27 envs, 256 threads, on 444 slots) leaves the GPU two-thirds empty for the second half of the kernel:
+            // 59.4 us against 46.8 for 863 blocks of 19 envs on the 888 slots of 128-thread blocks, 46.5 for 443 blocks of 37 envs
+            // at 256 threads (profiles/r2/ab_march_31_tail2_waves.jsonl).  So: 128-thread blocks of up to 47 agents, and as many
+            // envs per block as fill a whole number of waves.
+            static int per_sm = 0;                          // resident 128-thread blocks per SM
+            if (per_sm == 0) {
+                const size_t sm0 = (size_t)(47 / sim->num_agents) * sim->num_agents * (sim->num_agents - 1) * sizeof(TailTask);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail2, 128, sm0) != cudaSuccess || per_sm < 1) { per_sm = -1; cudaGetLastError(); }
+            }
+            if (per_sm > 0) {
+                const long long cap = (long long)per_sm * num_sms();
+                const long long emax = max(1, 47 / sim->num_agents);
+                const long long waves = (sim->num_envs + cap * emax - 1) / (cap * emax);
+                epb = (int)((sim->num_envs + waves * cap - 1) / (waves * cap));
+                t2 = 128;
+            }
+        }
+        const size_t smem = (size_t)epb * sim->num_agents * (sim->num_agents - 1) * sizeof(TailTask);
         launch_k(k_tail2, dim3((sim->num_envs + epb - 1) / epb), dim3(t2), smem, st, g_pdl_this_step && lean, *sim, bv,
                  fused ? (int)tail->env_level : 0, fused ? tail->ar : no_ar, max_scan, epb);
         LAUNCH_CHECK("k_tail2");

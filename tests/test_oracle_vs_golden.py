@@ -107,7 +107,7 @@ def test_scans_wide(name):
                 assert np.array_equal(oracle.get_scan(m, p, B, 4.7), ref)
 
 
-@pytest.mark.parametrize('name', ['traj_a1_random', 'traj_a2_random', 'traj_a2_close', 'traj_a3_euler'])
+@pytest.mark.parametrize('name', ['traj_a1_random', 'traj_a2_random', 'traj_a2_close', 'traj_a3_euler', 'traj_a4_train'])
 def test_trajectories(example_map, name):
     k = g(name + '.npz')
     E, T, A = k['actions'].shape[:3]
@@ -125,7 +125,7 @@ def test_trajectories(example_map, name):
             n_col += int(sim.collisions.sum())
             if (e, t) in ticks:
                 assert np.max(np.abs(sim.scans - k['scans'][ticks[(e, t)]])) < 1e-9, (e, t)
-    if name == 'traj_a2_close':
+    if name in ('traj_a2_close', 'traj_a4_train'):      # (a4: four cars nose to tail, make_golden_a4.py)
         assert n_col > 0
 
 

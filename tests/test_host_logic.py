@@ -93,6 +93,32 @@ def test_library_exports_every_declared_symbol():
     assert L.f110_scan(ctypes.byref(nat.F110Map()), ctypes.byref(nat.F110Beams()), None, 1, None, None, None, None) == -2
 
 
+def test_march_kernel_resource_budget():
+    """The production ray-march kernels must keep the register and stack budget the measurements were taken with: 32 registers
+    (64 warps per SM) and at most 24 bytes of stack per thread.  A same-results build whose caller-side spills grew to 56 bytes of
+    stack was 13 % slower (profiles/r2/README.md, "What ptxas does to this kernel"): this is the check to run after any edit to
+    csrc/march_lean.cuh, before spending GPU time."""
+    import shutil
+    from f1tenth_gym_b200 import _native as nat
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(tool):
+        pytest.skip('cuobjdump not available')
+    nat.lib()
+    lib_path = os.path.join(os.path.dirname(os.path.abspath(nat.__file__)), 'libf110_b200.so')
+    out = subprocess.run([tool, '-res-usage', lib_path], capture_output=True, text=True).stdout
+    usage = {}
+    for fn, reg, stack in re.findall(r'Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)', out):
+        usage[fn] = (int(reg), int(stack))
+    # k_march_lean<TABLE=0, NOISE=0, COUNT=0, CELLS=1, LAYERED=0, 512 threads, 4 blocks/SM, DYN=1, CL=1, IPT, RING=2>: the default
+    # launches of the dynamic queue (4 / 2 entries per ticket, ticket size by run class)
+    for ipt in (4, 2, 0):
+        name = '_ZN4f11012k_march_leanILi0ELb0ELb0ELb1ELb0ELi512ELi4ELb1ELi1ELi%dELi2EEEvNS_5LeanKENS_10MarchQueueE' % ipt
+        assert name in usage, name
+        reg, stack = usage[name]
+        assert reg <= 32, (name, reg)
+        assert stack <= 24, (name, stack)
+
+
 def test_ctypes_structs_match_c_layout(tmp_path):
     from f1tenth_gym_b200 import _native as nat
     structs = {'f110_map': nat.F110Map, 'f110_beams': nat.F110Beams, 'f110_sim': nat.F110Sim,

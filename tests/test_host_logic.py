@@ -119,6 +119,23 @@ def test_march_kernel_resource_budget():
         assert stack <= 24, (name, stack)
 
 
+def test_sass_carries_the_sm100a_paths():
+    """The built library is sm_100a code and contains what DESIGN.md says it does: the TMA tile load of the north_star march variant
+    (UTMALDG with mbarrier SYNCS), the elect.sync queue pop (ELECT) and the programmatic-dependent-launch hooks (ACQBULK / PREEXIT)."""
+    import shutil
+    from f1tenth_gym_b200 import _native as nat
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(tool):
+        pytest.skip('cuobjdump not available')
+    nat.lib()
+    lib_path = os.path.join(os.path.dirname(os.path.abspath(nat.__file__)), 'libf110_b200.so')
+    elf = subprocess.run([tool, '-lelf', lib_path], capture_output=True, text=True).stdout
+    assert 'sm_100a' in elf, elf
+    sass = subprocess.run([tool, '-sass', lib_path], capture_output=True, text=True).stdout
+    for mnemonic in ('UTMALDG', 'SYNCS', 'ELECT', 'ACQBULK', 'PREEXIT', 'DADD.RM'):
+        assert mnemonic in sass, mnemonic
+
+
 def test_ctypes_structs_match_c_layout(tmp_path):
     from f1tenth_gym_b200 import _native as nat
     structs = {'f110_map': nat.F110Map, 'f110_beams': nat.F110Beams, 'f110_sim': nat.F110Sim,

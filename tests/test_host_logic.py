@@ -136,6 +136,19 @@ def test_sass_carries_the_sm100a_paths():
         assert mnemonic in sass, mnemonic
 
 
+def test_unpack_scans_u24_roundtrip():
+    """Host decoder of the opt-in 24-bit scan block (f110_pack_scans_u24: round(range * 2^19), little-endian 3 bytes): 2^-19 m
+    steps, 32 m of range, |error| <= 2^-20 m + fp32 rounding -- far inside the 1e-4 m parity tolerance."""
+    from f1tenth_gym_b200.simulator import Simulator
+    rng = np.random.default_rng(3)
+    r = np.concatenate([rng.uniform(0.0, 30.0, 5000), [0.0, 30.0, 2.0 ** -19, 31.999998]])
+    q = np.rint(r * 2.0 ** 19).astype(np.uint32)
+    buf = np.stack([q & 255, (q >> 8) & 255, (q >> 16) & 255], axis=-1).astype(np.uint8)
+    dec = Simulator.unpack_scans_u24(buf)
+    assert dec.dtype == np.float32 and dec.shape == r.shape
+    assert np.max(np.abs(dec.astype(np.float64) - r)) <= 2.0 ** -20 + 30.0 * 2.0 ** -24
+
+
 def test_ctypes_structs_match_c_layout(tmp_path):
     from f1tenth_gym_b200 import _native as nat
     structs = {'f110_map': nat.F110Map, 'f110_beams': nat.F110Beams, 'f110_sim': nat.F110Sim,
